@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py — occlusion Mrays/s of the fused AO trace (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--workload c2|c1|c3|c4]
+
+A "step" is one pass of the hot path (bake::computeAO's ray generation + any-hit traversal +
+accumulation) over the whole sample set of the workload.  At N = 1 the workload is
+BASELINE.json configs[1]: the procedural 1M-triangle heightfield, 3 samples/face (3.0 M
+samples), 256 rays/sample = 770 M rays per step.  For N > 1 the scene (and its BVH) is
+replicated and the sample set grows to N x 3.0 M (weak scaling); rank r traces the contiguous
+global range [r*n/N, (r+1)*n/N) with no data-path collective (RNG streams are functions of the
+global sample index).
+
+value : whole-job Mrays/s, device-timed (CUDA events on the launch stream, max over ranks),
+        samples + BVH resident in HBM.
+e2e   : the same metric through the reference-facing call computeAO(scene, blockers, samples,
+        rays, offset, maxdist) -> ao with HOST (pinned) buffers: scene upload + BVH build +
+        sample upload + trace + AO download, every step, wall clock, max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from optix_prime_baking_b200 import scenes  # noqa: E402
+
+RAYS = {"c1": 64, "c2": 256, "c3": 1024, "c4": 256}
+
+
+def make_workload(name: str):
+    if name == "c1":
+        scene, blockers = scenes.config1_sphere()
+        return scene, blockers, 3, 0, "sphere-on-ground-plane 79.6k tris, 3 samples/face, 64 rays/sample"
+    if name == "c2":
+        scene, blockers = scenes.config2_heightfield()
+        return scene, blockers, 3, 0, "procedural 1M-tri heightfield (708x708 cells), 3 samples/face, 256 rays/sample"
+    if name == "c3":
+        scene, blockers = scenes.config3_bigmesh()
+        return scene, blockers, 0, 10_000_000, "20M-tri warped heightfield, 10M area-weighted samples, 1024 rays/sample"
+    if name == "c4":
+        scene, blockers = scenes.config4_instanced()
+        return scene, blockers, 3, 0, "1000 instances of a 49.6k-tri mesh (TLAS/BLAS), 3 samples/face, 256 rays/sample"
+    raise SystemExit(f"unknown workload {name}")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device_index: int):
+        self.idx = device_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def pinned_like(a: np.ndarray) -> np.ndarray:
+    import torch
+    t = torch.empty(a.shape, dtype=torch.from_numpy(np.empty(0, dtype=a.dtype)).dtype, pin_memory=True)
+    out = t.numpy()
+    out[...] = a
+    out_holder.append(t)
+    return out
+
+
+out_holder = []
+
+
+def cpu_baseline(scene, blockers, samples, rays, off, maxd, target_rays=12_000_000):
+    """The oracle (kind 'port': the reference cannot be compiled) on all host cores,
+    on a bounded, strided subset of the workload's samples."""
+    from tests.oracle_binding import Oracle, lib
+    from optix_prime_baking_b200.ctypes_types import SampleBuffers
+    q = int(np.float32(np.sqrt(np.float32(rays))) + np.float32(0.5))
+    n_sub = max(1, min(samples.n, target_rays // (q * q)))
+    pick = np.linspace(0, samples.n - 1, n_sub).astype(np.int64)
+    sub = SampleBuffers(n_sub)
+    sub.positions[...] = samples.positions[pick]
+    sub.normals[...] = samples.normals[pick]
+    sub.face_normals[...] = samples.face_normals[pick]
+    orc = Oracle(scene, blockers)
+    t0 = time.perf_counter()
+    _ = orc.tracer
+    t_build = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    ao, hits = orc.compute_ao(sub, rays, off, maxd)
+    dt = time.perf_counter() - t0
+    cores = lib().ao_oracle_num_threads()
+    orc.close()
+    return {"value": n_sub * q * q / dt / 1e6, "unit": "Mrays/s", "cores": int(cores), "kind": "port",
+            "sample": f"{n_sub} evenly strided samples x {q * q} rays = {n_sub * q * q} rays of the same workload "
+                      f"(oracle BVH build {t_build:.1f} s excluded)", "seconds": dt}, sub, hits
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path.  The reference cannot be built (no sources,
+    closed OptiX Prime), so this times the oracle port with all host threads on bounded samples."""
+    if rank != 0:
+        return
+    scene, blockers, min_per, requested, desc = make_workload(args.workload)
+    rays = RAYS[args.workload]
+    off, maxd = scenes.default_distances(scene)
+    from tests.oracle_binding import Oracle, lib
+    orc = Oracle(scene, blockers)
+    total, per = orc.distribute_samples(min_per, requested)
+    samples = orc.sample_instances(per, min_per)
+    q = int(np.float32(np.sqrt(np.float32(rays))) + np.float32(0.5))
+    n_sub = max(1, min(samples.n, 6_000_000 // (q * q)))
+    _ = orc.tracer
+    from optix_prime_baking_b200.ctypes_types import SampleBuffers
+    times = []
+    for s in range(args.warmup + args.steps):
+        pick = (np.linspace(0, samples.n - 1, n_sub).astype(np.int64) + s) % samples.n
+        sub = SampleBuffers(n_sub)
+        sub.positions[...] = samples.positions[pick]
+        sub.normals[...] = samples.normals[pick]
+        sub.face_normals[...] = samples.face_normals[pick]
+        t0 = time.perf_counter()
+        orc.compute_ao(sub, rays, off, maxd)
+        if s >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    dt = float(np.mean(times))
+    val = n_sub * q * q / dt / 1e6
+    cores = int(lib().ao_oracle_num_threads())
+    sample = f"{n_sub} strided samples x {q * q} rays per step"
+    print(json.dumps({
+        "impl": "reference", "metric": "occlusion Mrays/s", "value": val, "unit": "Mrays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "note": "reference sources absent (SURVEY.md §0): CPU oracle port on host cores"},
+        "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="c2", choices=list(RAYS))
+    ap.add_argument("--trace-kernel", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from optix_prime_baking_b200 import api
+    from optix_prime_baking_b200.ctypes_types import SampleBuffers
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n_gpus = world
+
+    scene, blockers, min_per, requested, desc = make_workload(args.workload)
+    rays = RAYS[args.workload]
+    off, maxd = scenes.default_distances(scene)
+    q = int(np.float32(np.sqrt(np.float32(rays))) + np.float32(0.5))
+
+    bk = api.Baker(device=local_rank, trace_kernel=args.trace_kernel)
+    stream = torch.cuda.current_stream()
+    bk.set_stream(stream.cuda_stream)
+    bk.set_scene(scene, blockers)
+    base_total, _ = bk.distribute_samples(min_per, requested)
+    # weak scaling: N x the single-GPU sample budget over the same (replicated) scene
+    total, per = bk.distribute_samples(min_per, base_total * n_gpus) if n_gpus > 1 else bk.distribute_samples(min_per, requested)
+    bk.sample_instances(per, min_per, download=False)
+    begin, end = rank * total // n_gpus, (rank + 1) * total // n_gpus
+    rays_rank = (end - begin) * q * q
+    st = bk.stats()
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def step():
+        bk.compute_ao(rays, off, maxd, download=False, begin=begin, end=end)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        flush.zero_()
+        step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kernel_ms = []
+    for a, b in ev:
+        flush.zero_()          # L2 flush between timed iterations (outside the event pair)
+        a.record(stream)
+        step()
+        b.record(stream)
+        kernel_ms.append(bk.timings().trace_ms)
+    barrier()
+    clocks = sampler.stop()
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    tot_rays = torch.tensor([float(rays_rank)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot_rays, op=dist.ReduceOp.SUM)
+    ms_total = float(t.item())
+    rays_job = float(tot_rays.item())
+    value = rays_job * args.steps / (ms_total * 1e-3) / 1e6
+
+    # ---- e2e: computeAO with host (pinned) buffers, incl. BVH build, every step ----
+    samples_host = SampleBuffers(end - begin)
+    full = SampleBuffers(total) if n_gpus == 1 else None
+    # fetch this rank's samples once (untimed) to act as the caller's host arrays
+    tmp = bk.sample_instances(per, min_per, download=True)
+    for name in ("positions", "normals", "face_normals"):
+        getattr(samples_host, name)[...] = getattr(tmp, name)[begin:end]
+    del tmp, full
+    pin = SampleBuffers.__new__(SampleBuffers)
+    pin.n = samples_host.n
+    pin.positions = pinned_like(samples_host.positions)
+    pin.normals = pinned_like(samples_host.normals)
+    pin.face_normals = pinned_like(samples_host.face_normals)
+    pin.infos = samples_host.infos
+    import ctypes as C
+    from optix_prime_baking_b200.ctypes_types import AoSamples
+    pin.c = AoSamples(pin.n, pin.positions.ctypes.data, pin.normals.ctypes.data, pin.face_normals.ctypes.data, None)
+    ao_host = pinned_like(np.zeros(pin.n, dtype=np.float32))
+    h2d = sum(m.vertices.nbytes + m.tris.nbytes + (m.normals.nbytes if m.normals is not None else 0) for m in scene.meshes)
+    h2d += sum(m.vertices.nbytes + m.tris.nbytes for m in blockers.meshes) + 36 * pin.n
+    d2h = 4 * pin.n
+    e2e_times = []
+    for s in range(1 + args.e2e_steps):
+        barrier()
+        t0 = time.perf_counter()
+        with api.Baker(device=local_rank, trace_kernel=args.trace_kernel) as b2:
+            b2.set_scene(scene, blockers)
+            b2.set_samples(pin)
+            b2.compute_ao(rays, off, maxd, download=True, out=ao_host)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if s >= 1:
+            e2e_times.append(dt)
+    te = torch.tensor([float(np.mean(e2e_times))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = rays_job / float(te.item()) / 1e6
+
+    # ---- roofline of the dominant kernel (the fused AO kernel) ----
+    with api.Baker(device=local_rank, collect_stats=True, trace_kernel=args.trace_kernel) as b3:
+        b3.set_scene(scene, blockers)
+        b3.set_samples(pin)
+        n_probe = min(pin.n, 200_000)
+        b3.compute_ao(rays, off, maxd, download=False, begin=0, end=n_probe)
+        s3 = b3.stats()
+    nodes_per_ray = s3.node_visits / max(s3.rays, 1)
+    tris_per_ray = s3.triangle_tests / max(s3.rays, 1)
+    insts_per_ray = s3.instance_entries / max(s3.rays, 1)
+    bytes_per_ray = 80.0 * nodes_per_ray + 48.0 * tris_per_ray + 64.0 * insts_per_ray + 40.0 / (q * q)
+    kms = float(np.mean(kernel_ms))
+    achieved = rays_rank * bytes_per_ray / (kms * 1e-3) / 1e9
+    peak, peak_src = peaks()
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get(args.workload)
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline:
+            cpu, _, _ = cpu_baseline(scene, blockers, samples_host, rays, off, maxd)
+        line = {
+            "metric": "occlusion Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "samples_total": int(total), "rays_per_step": int(rays_job),
+                       "bvh": f"{st.num_bvh_nodes} 8-wide nodes + {st.num_bvh_triangles} tris = {st.bvh_bytes / 1e6:.1f} MB, "
+                              f"{'TLAS/BLAS' if st.two_level else 'flattened'}, replicated per GPU",
+                       "sharding": "contiguous global sample ranges, no data-path collective",
+                       "l2": "256 MB flush write between timed iterations; BVH + samples exceed the 126 MB L2",
+                       "trace_kernel": args.trace_kernel},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "what": "computeAO(scene, blockers, samples) with pinned host buffers: scene upload + BVH build + "
+                            "sample upload + trace + AO download", "seconds_per_step": float(te.item())},
+            "gpu_launches": 2 * args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "k_ao (fused raygen+traverse+accumulate)",
+                         "kernel_ms": kms, "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray,
+                         "tris_per_ray": tris_per_ray, "instances_per_ray": insts_per_ray,
+                         "note": "algorithmic bytes = 80 B/node visit + 48 B/triangle test + 64 B/instance entry + 40 B/sample "
+                                 "(SURVEY §8d); traversal is latency/L2 bound, see DESIGN.md"},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,467 @@
+// aob_bvh.cuh — 8-wide compressed BVH: node layout, LBVH construction bodies, SAH-guided
+// collapse, and any-hit traversal.  Replaces the closed OptiX Prime builder + traversal the
+// reference called through rtpModelUpdate / rtpQueryExecute (bake_ao_optix_prime.cpp;
+// SURVEY §8 a10/a11).
+//
+// Layout (HBM):
+//   nodes : 80-byte Node8 records = 5 x 16-byte loads (Ylitie, Karras, Laine 2017 style
+//           compressed wide BVH): parent-relative 8-bit child boxes, a shared power-of-two
+//           scale per axis, an internal-child mask, and a meta byte per slot.
+//   tris  : 48-byte records = 3 x float4 (v0, v1, v2; w lanes carry the source primitive id),
+//           in leaf order, so a leaf is (prim_base + offset, count <= 3).
+//   insts : 64-byte records = 3 x float4 rows of the world->object 3x4 + uint4{blas_root,..}.
+//
+// Kernel bodies are written as `*_body(tid, ...)` functions that also compile under plain
+// g++ (AOB_HOST_EMU) — tests/emu runs the identical code serially on the CPU.
+#pragma once
+#include "aob_math.cuh"
+#include <string.h>
+
+namespace aob {
+
+// ---- host/device shims ---------------------------------------------------------------
+struct alignas(16) U4 { uint32_t x, y, z, w; };
+struct alignas(16) F4 { float x, y, z, w; };
+struct alignas(8) U2 { uint32_t x, y; };
+
+#if defined(__CUDA_ARCH__)
+AOB_D U4 ld_u4(const U4* p) { uint4 v = __ldg(reinterpret_cast<const uint4*>(p)); U4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r; }
+AOB_D F4 ld_f4(const F4* p) { float4 v = __ldg(reinterpret_cast<const float4*>(p)); F4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r; }
+AOB_D F4 ld_f4_cg(const F4* p) { float4 v = __ldcg(reinterpret_cast<const float4*>(p)); F4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r; }
+AOB_D float as_float(uint32_t u) { return __uint_as_float(u); }
+AOB_D uint32_t as_uint(float f) { return __float_as_uint(f); }
+AOB_D uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t s) { return __byte_perm(a, b, s); }
+AOB_D int clz32(uint32_t v) { return __clz((int)v); }
+AOB_D int clz64(uint64_t v) { return __clzll((long long)v); }
+AOB_D int popc32(uint32_t v) { return __popc(v); }
+AOB_D int ffs32(uint32_t v) { return __ffs((int)v); }
+AOB_D uint32_t atomic_add_u32(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
+AOB_D void thread_fence() { __threadfence(); }
+#else
+inline U4 ld_u4(const U4* p) { return *p; }
+inline F4 ld_f4(const F4* p) { return *p; }
+inline F4 ld_f4_cg(const F4* p) { return *p; }
+inline float as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+inline uint32_t as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+inline uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t s) {
+  uint64_t v = ((uint64_t)b << 32) | a;
+  uint32_t r = 0;
+  for (int i = 0; i < 4; i++) r |= (uint32_t)((v >> (8 * ((s >> (4 * i)) & 7))) & 0xff) << (8 * i);
+  return r;
+}
+inline int clz32(uint32_t v) { return v ? __builtin_clz(v) : 32; }
+inline int clz64(uint64_t v) { return v ? __builtin_clzll(v) : 64; }
+inline int popc32(uint32_t v) { return __builtin_popcount(v); }
+inline int ffs32(uint32_t v) { return __builtin_ffs((int)v); }
+inline uint32_t atomic_add_u32(uint32_t* p, uint32_t v) { uint32_t o = *p; *p += v; return o; }
+inline void thread_fence() {}
+#endif
+
+// ---- node layout ---------------------------------------------------------------------
+struct alignas(16) Node8 {
+  float px, py, pz;            // quantisation origin = node box min
+  uint8_t ex, ey, ez;          // biased fp32 exponents of the per-axis grid step
+  uint8_t imask;               // bit s: slot s holds an internal child
+  uint32_t child_base;         // index of the first internal child (children contiguous, slot order)
+  uint32_t prim_base;          // index of the first leaf primitive referenced by this node
+  uint8_t meta[8];             // 0 empty | internal: 0x20|(24+slot) | leaf: unary(count)<<5 | offset
+  uint8_t qlox[8], qloy[8], qloz[8];
+  uint8_t qhix[8], qhiy[8], qhiz[8];
+};
+static_assert(sizeof(Node8) == 80, "Node8 must be 80 bytes");
+
+constexpr uint32_t kLeafBit = 0x80000000u;
+constexpr uint32_t kSentinel = 0xFFFFFFFFu;
+constexpr int kStackSize = 48;
+
+struct BvhView {
+  const U4* nodes;   // 5 x U4 per node
+  const F4* tris;    // 3 x F4 per triangle
+  const F4* insts;   // 4 x F4 per instance (two-level only)
+  uint32_t root;     // node index where traversal starts (TLAS root when two_level)
+  uint32_t two_level;
+};
+
+// =======================================================================================
+// Construction bodies
+// =======================================================================================
+AOB_HD uint64_t expand21(uint32_t v) {  // spread the low 21 bits to every third bit
+  uint64_t x = v & 0x1fffffu;
+  x = (x | x << 32) & 0x1f00000000ffffull;
+  x = (x | x << 16) & 0x1f0000ff0000ffull;
+  x = (x | x << 8) & 0x100f00f00f00f00full;
+  x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+  x = (x | x << 2) & 0x1249249249249249ull;
+  return x;
+}
+// 63-bit Morton code of the box centroid inside the centroid bounds [cmin, cmin + 1/cinv].
+AOB_HD uint64_t morton63(F4 lo, F4 hi, V3 cmin, V3 cinv) {
+  float cx = 0.5f * (lo.x + hi.x), cy = 0.5f * (lo.y + hi.y), cz = 0.5f * (lo.z + hi.z);
+  float fx = fminf(fmaxf((cx - cmin.x) * cinv.x, 0.0f), 1.0f);
+  float fy = fminf(fmaxf((cy - cmin.y) * cinv.y, 0.0f), 1.0f);
+  float fz = fminf(fmaxf((cz - cmin.z) * cinv.z, 0.0f), 1.0f);
+  uint32_t ix = (uint32_t)fminf(fx * 2097152.0f, 2097151.0f);
+  uint32_t iy = (uint32_t)fminf(fy * 2097152.0f, 2097151.0f);
+  uint32_t iz = (uint32_t)fminf(fz * 2097152.0f, 2097151.0f);
+  return (expand21(ix) << 2) | (expand21(iy) << 1) | expand21(iz);
+}
+
+// Binary LBVH arrays (Karras 2012).  n leaves, n-1 internal nodes; node refs carry kLeafBit.
+struct Lbvh {
+  const uint64_t* keys;   // sorted Morton keys [n]
+  const uint32_t* prim;   // sorted primitive ids [n]
+  const F4* plo;          // primitive boxes (indexed by primitive id)
+  const F4* phi;
+  uint32_t* left;         // [n-1]
+  uint32_t* right;        // [n-1]
+  uint32_t* first;        // [n-1] first leaf of the node's range
+  uint32_t* last;         // [n-1]
+  uint32_t* parent_int;   // [n-1]
+  uint32_t* parent_leaf;  // [n]
+  F4* ilo;                // [n-1] internal boxes
+  F4* ihi;
+  uint32_t* flags;        // [n-1] zeroed arrival counters
+  uint32_t n;
+};
+
+AOB_HD int lbvh_delta(const Lbvh& L, int i, int j) {
+  if (j < 0 || j >= (int)L.n) return -1;
+  uint64_t a = L.keys[i], b = L.keys[j];
+  if (a == b) return 64 + clz32((uint32_t)i ^ (uint32_t)j);
+  return clz64(a ^ b);
+}
+// one thread per internal node i in [0, n-1)
+AOB_HD void lbvh_hierarchy_body(uint32_t tid, const Lbvh& L) {
+  if (tid + 1 >= L.n) return;
+  const int i = (int)tid;
+  const int d = (lbvh_delta(L, i, i + 1) - lbvh_delta(L, i, i - 1)) >= 0 ? 1 : -1;
+  const int dmin = lbvh_delta(L, i, i - d);
+  int lmax = 2;
+  while (lbvh_delta(L, i, i + lmax * d) > dmin) lmax *= 2;
+  int l = 0;
+  for (int t = lmax / 2; t >= 1; t /= 2)
+    if (lbvh_delta(L, i, i + (l + t) * d) > dmin) l += t;
+  const int j = i + l * d;
+  const int dnode = lbvh_delta(L, i, j);
+  int s = 0;
+  int t = l;
+  do {
+    t = (t + 1) >> 1;
+    if (lbvh_delta(L, i, i + (s + t) * d) > dnode) s += t;
+  } while (t > 1);
+  const int gamma = i + s * d + (d < 0 ? d : 0);
+  const int lo = i < j ? i : j, hi = i < j ? j : i;
+  uint32_t lref, rref;
+  if (lo == gamma) { lref = (uint32_t)gamma | kLeafBit; L.parent_leaf[gamma] = (uint32_t)i; }
+  else { lref = (uint32_t)gamma; L.parent_int[gamma] = (uint32_t)i; }
+  if (hi == gamma + 1) { rref = (uint32_t)(gamma + 1) | kLeafBit; L.parent_leaf[gamma + 1] = (uint32_t)i; }
+  else { rref = (uint32_t)(gamma + 1); L.parent_int[gamma + 1] = (uint32_t)i; }
+  L.left[i] = lref;
+  L.right[i] = rref;
+  L.first[i] = (uint32_t)lo;
+  L.last[i] = (uint32_t)hi;
+  if (i == 0) L.parent_int[0] = kSentinel;
+}
+
+AOB_HD void lbvh_ref_box(const Lbvh& L, uint32_t ref, F4* lo, F4* hi) {
+  if (ref & kLeafBit) {
+    uint32_t p = L.prim[ref & ~kLeafBit];
+    *lo = L.plo[p]; *hi = L.phi[p];
+  } else {
+    *lo = L.ilo[ref]; *hi = L.ihi[ref];
+  }
+}
+// one thread per leaf: walk up, the second arrival at a node computes its box.
+AOB_HD void lbvh_refit_body(uint32_t tid, const Lbvh& L) {
+  if (tid >= L.n || L.n < 2) return;
+  uint32_t cur = L.parent_leaf[tid];
+  while (cur != kSentinel) {
+    thread_fence();
+    if (atomic_add_u32(&L.flags[cur], 1u) == 0u) return;
+    thread_fence();
+    // internal child boxes were written by other threads: read them through L2 (ld.cg)
+    F4 alo, ahi, blo, bhi;
+    const uint32_t lr = L.left[cur], rr = L.right[cur];
+    if (lr & kLeafBit) { const uint32_t p = L.prim[lr & ~kLeafBit]; alo = L.plo[p]; ahi = L.phi[p]; }
+    else { alo = ld_f4_cg(&L.ilo[lr]); ahi = ld_f4_cg(&L.ihi[lr]); }
+    if (rr & kLeafBit) { const uint32_t p = L.prim[rr & ~kLeafBit]; blo = L.plo[p]; bhi = L.phi[p]; }
+    else { blo = ld_f4_cg(&L.ilo[rr]); bhi = ld_f4_cg(&L.ihi[rr]); }
+    F4 lo, hi;
+    lo.x = fminf(alo.x, blo.x); lo.y = fminf(alo.y, blo.y); lo.z = fminf(alo.z, blo.z); lo.w = 0.f;
+    hi.x = fmaxf(ahi.x, bhi.x); hi.y = fmaxf(ahi.y, bhi.y); hi.z = fmaxf(ahi.z, bhi.z); hi.w = 0.f;
+    L.ilo[cur] = lo;
+    L.ihi[cur] = hi;
+    cur = L.parent_int[cur];
+  }
+}
+
+AOB_HD float box_half_area(F4 lo, F4 hi) {
+  float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+  return dx * dy + dy * dz + dz * dx;
+}
+AOB_HD uint32_t lbvh_ref_count(const Lbvh& L, uint32_t ref) {
+  return (ref & kLeafBit) ? 1u : (L.last[ref] - L.first[ref] + 1u);
+}
+
+// smallest biased exponent e with 255 * 2^(e-127) >= extent (0 when extent == 0)
+AOB_HD uint32_t quant_exponent(float extent) {
+  if (!(extent > 0.0f)) return 0u;
+  float s = (extent / 255.0f) * 1.000001f;
+  uint32_t b = as_uint(s);
+  uint32_t e = (b >> 23) & 0xffu;
+  if (b & 0x7fffffu) e += 1u;
+  if (e < 1u) e = 1u;
+  if (e > 254u) e = 254u;
+  return e;
+}
+AOB_HD void quantize_axis(float p, uint32_t e, float clo, float chi, uint8_t* qlo, uint8_t* qhi) {
+  const float scale = as_float(e << 23);
+  if (!(scale > 0.0f)) { *qlo = 0; *qhi = 0; return; }
+  int lo = (int)floorf((clo - p) / scale);
+  int hi = (int)ceilf((chi - p) / scale);
+  lo = lo < 0 ? 0 : (lo > 255 ? 255 : lo);
+  hi = hi < 0 ? 0 : (hi > 255 ? 255 : hi);
+  while (lo > 0 && p + (float)lo * scale > clo) lo--;
+  while (hi < 255 && p + (float)hi * scale < chi) hi++;
+  *qlo = (uint8_t)lo;
+  *qhi = (uint8_t)hi;
+}
+
+struct CollapseArgs {
+  Lbvh L;
+  Node8* nodes;          // absolute array
+  uint32_t* wide2bin;    // wide node index (relative to node_offset) -> binary node ref
+  uint32_t* leaf_prims;  // leaf order (relative to prim_offset) -> primitive id
+  uint32_t* node_count;  // relative counters (start at 1 / 0)
+  uint32_t* prim_count;
+  uint32_t node_offset;  // added to child_base
+  uint32_t prim_offset;  // added to prim_base
+  uint32_t max_leaf;     // primitives per leaf slot: 3 for triangles, 1 for instances
+};
+
+// one thread per wide node w (relative index) of the current level.
+AOB_HD void collapse_body(uint32_t w, const CollapseArgs& A) {
+  const Lbvh& L = A.L;
+  const uint32_t bref = A.wide2bin[w];
+  uint32_t slot[8];
+  float area[8];
+  int ns = 0;
+  F4 nlo, nhi;
+  if ((bref & kLeafBit) || lbvh_ref_count(L, bref) <= A.max_leaf) {
+    // degenerate root: the whole tree fits one leaf slot
+    lbvh_ref_box(L, bref, &nlo, &nhi);
+    slot[0] = bref; area[0] = -1.0f; ns = 1;
+  } else {
+    nlo = L.ilo[bref]; nhi = L.ihi[bref];
+    slot[0] = L.left[bref]; slot[1] = L.right[bref]; ns = 2;
+    for (int k = 0; k < 2; k++) {
+      F4 lo, hi;
+      lbvh_ref_box(L, slot[k], &lo, &hi);
+      area[k] = (lbvh_ref_count(L, slot[k]) <= A.max_leaf) ? -1.0f : box_half_area(lo, hi);
+    }
+    // greedy surface-area-ordered expansion (the SAH heuristic of the wide collapse): open the
+    // largest openable child until 8 slots are used.
+    while (ns < 8) {
+      int best = -1;
+      float ba = -1.0f;
+      for (int k = 0; k < ns; k++)
+        if (area[k] > ba) { ba = area[k]; best = k; }
+      if (best < 0) break;
+      const uint32_t b = slot[best];
+      const uint32_t c0 = L.left[b], c1 = L.right[b];
+      slot[best] = c0;
+      slot[ns] = c1;
+      const int idx[2] = {best, ns};
+      ns++;
+      for (int k = 0; k < 2; k++) {
+        F4 lo, hi;
+        lbvh_ref_box(L, slot[idx[k]], &lo, &hi);
+        area[idx[k]] = (lbvh_ref_count(L, slot[idx[k]]) <= A.max_leaf) ? -1.0f : box_half_area(lo, hi);
+      }
+    }
+  }
+  // classify and allocate
+  uint32_t n_int = 0, n_prims = 0;
+  for (int k = 0; k < ns; k++) {
+    if (area[k] >= 0.0f) n_int++;
+    else n_prims += lbvh_ref_count(L, slot[k]);
+  }
+  uint32_t cbase = n_int ? atomic_add_u32(A.node_count, n_int) : 0u;
+  uint32_t pbase = n_prims ? atomic_add_u32(A.prim_count, n_prims) : 0u;
+  Node8 nd;
+  nd.px = nlo.x; nd.py = nlo.y; nd.pz = nlo.z;
+  const uint32_t ex = quant_exponent(nhi.x - nlo.x), ey = quant_exponent(nhi.y - nlo.y), ez = quant_exponent(nhi.z - nlo.z);
+  nd.ex = (uint8_t)ex; nd.ey = (uint8_t)ey; nd.ez = (uint8_t)ez;
+  nd.child_base = A.node_offset + cbase;
+  nd.prim_base = A.prim_offset + pbase;
+  uint32_t imask = 0, ci = 0, po = 0;
+  for (int k = 0; k < 8; k++) {
+    if (k >= ns) {
+      nd.meta[k] = 0;
+      nd.qlox[k] = nd.qloy[k] = nd.qloz[k] = 255;
+      nd.qhix[k] = nd.qhiy[k] = nd.qhiz[k] = 0;
+      continue;
+    }
+    F4 lo, hi;
+    lbvh_ref_box(L, slot[k], &lo, &hi);
+    quantize_axis(nlo.x, ex, lo.x, hi.x, &nd.qlox[k], &nd.qhix[k]);
+    quantize_axis(nlo.y, ey, lo.y, hi.y, &nd.qloy[k], &nd.qhiy[k]);
+    quantize_axis(nlo.z, ez, lo.z, hi.z, &nd.qloz[k], &nd.qhiz[k]);
+    if (area[k] >= 0.0f) {
+      imask |= 1u << k;
+      nd.meta[k] = (uint8_t)(0x20u | (24u + (uint32_t)k));
+      A.wide2bin[cbase + ci] = slot[k];
+      ci++;
+    } else {
+      const uint32_t cnt = lbvh_ref_count(L, slot[k]);
+      const uint32_t f = (slot[k] & kLeafBit) ? (slot[k] & ~kLeafBit) : L.first[slot[k]];
+      for (uint32_t c = 0; c < cnt; c++) A.leaf_prims[pbase + po + c] = L.prim[f + c];
+      nd.meta[k] = (uint8_t)((((1u << cnt) - 1u) << 5) | po);
+      po += cnt;
+    }
+  }
+  nd.imask = (uint8_t)imask;
+  A.nodes[A.node_offset + w] = nd;
+}
+
+// =======================================================================================
+// Traversal
+// =======================================================================================
+struct RayState {
+  V3 org, dir;
+  float tmin, tmax;
+  V3 idir;     // clamped reciprocal for the slab tests
+  Shear sh;
+};
+AOB_HD float safe_rcp(float d) {
+  const float tiny = 1e-18f;
+  float a = fabsf(d) > tiny ? d : (d < 0.0f ? -tiny : tiny);
+  return 1.0f / a;
+}
+AOB_HD void ray_setup(RayState& r, V3 org, V3 dir, float tmin, float tmax) {
+  r.org = org; r.dir = dir; r.tmin = tmin; r.tmax = tmax;
+  r.idir = v3(safe_rcp(dir.x), safe_rcp(dir.y), safe_rcp(dir.z));
+  r.sh = make_shear(dir);
+}
+
+AOB_D float q2f(uint32_t word, int k) {  // 32768 + byte k of word, as float (no int->float convert)
+  return as_float(byte_perm(word, 0x47000000u, 0x7404u | ((uint32_t)k << 4)));
+}
+
+// Slab-tests the 8 quantised child boxes of node `idx`; returns the hit mask in the layout
+// [31:24] internal slots | [23:0] leaf primitive bits.
+AOB_D uint32_t intersect_node8(const U4* nodes, uint32_t idx, const RayState& r, uint32_t* child_base,
+                               uint32_t* prim_base, uint32_t* imask) {
+  const U4* p = nodes + 5ull * idx;
+  const U4 n0 = ld_u4(p), n1 = ld_u4(p + 1), n2 = ld_u4(p + 2), n3 = ld_u4(p + 3), n4 = ld_u4(p + 4);
+  *child_base = n1.x;
+  *prim_base = n1.y;
+  *imask = n0.w >> 24;
+  const float adx = as_float((n0.w & 0xffu) << 23) * r.idir.x;
+  const float ady = as_float(((n0.w >> 8) & 0xffu) << 23) * r.idir.y;
+  const float adz = as_float(((n0.w >> 16) & 0xffu) << 23) * r.idir.z;
+  // t(q) = (32768 + q) * ad + (o - 32768 * ad); near/far padded by 2^-8 of a grid step, which
+  // bounds the rounding of the folded constant (see DESIGN.md "conservative slabs").
+  const float ox = (as_float(n0.x) - r.org.x) * r.idir.x - 32768.0f * adx;
+  const float oy = (as_float(n0.y) - r.org.y) * r.idir.y - 32768.0f * ady;
+  const float oz = (as_float(n0.z) - r.org.z) * r.idir.z - 32768.0f * adz;
+  const float padx = 0.00390625f * fabsf(adx), pady = 0.00390625f * fabsf(ady), padz = 0.00390625f * fabsf(adz);
+  const float onx = ox - padx, ofx = ox + padx, ony = oy - pady, ofy = oy + pady, onz = oz - padz, ofz = oz + padz;
+  const bool nx = r.dir.x < 0.0f, ny = r.dir.y < 0.0f, nz = r.dir.z < 0.0f;
+  uint32_t hitmask = 0;
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    const uint32_t lox = h ? n2.y : n2.x, loy = h ? n2.w : n2.z, loz = h ? n3.y : n3.x;
+    const uint32_t hix = h ? n3.w : n3.z, hiy = h ? n4.y : n4.x, hiz = h ? n4.w : n4.z;
+    const uint32_t meta = h ? n1.w : n1.z;
+    const uint32_t nwx = nx ? hix : lox, fwx = nx ? lox : hix;
+    const uint32_t nwy = ny ? hiy : loy, fwy = ny ? loy : hiy;
+    const uint32_t nwz = nz ? hiz : loz, fwz = nz ? loz : hiz;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const float tnx = fmaf(q2f(nwx, k), adx, onx), tfx = fmaf(q2f(fwx, k), adx, ofx);
+      const float tny = fmaf(q2f(nwy, k), ady, ony), tfy = fmaf(q2f(fwy, k), ady, ofy);
+      const float tnz = fmaf(q2f(nwz, k), adz, onz), tfz = fmaf(q2f(fwz, k), adz, ofz);
+      const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, r.tmin));
+      const float tf = fminf(fminf(tfx, tfy), fminf(tfz, r.tmax));
+      if (tn <= tf * 1.0000005f) {
+        const uint32_t m = (meta >> (8 * k)) & 0xffu;
+        hitmask |= (m >> 5) << (m & 31u);
+      }
+    }
+  }
+  return hitmask;
+}
+
+struct TraceCounters {
+  uint32_t nodes, tris, insts;
+};
+
+// Any-hit traversal of one ray with a caller-provided stack of kStackSize entries.
+template <bool STATS>
+AOB_D bool trace_any_hit(const BvhView& bvh, V3 org, V3 dir, float tmin, float tmax, U2* stack, TraceCounters* cnt) {
+  RayState r;
+  ray_setup(r, org, dir, tmin, tmax);
+  int sp = 0;
+  bool in_blas = !bvh.two_level;
+  U2 G;
+  G.x = bvh.root;
+  G.y = (1u << 24) | 1u;
+  while (true) {
+    U2 T;
+    if (G.y & 0xff000000u) {
+      const int bit = 31 - clz32(G.y);
+      G.y &= ~(1u << bit);
+      const uint32_t slot = (uint32_t)bit - 24u;
+      const uint32_t node = G.x + (uint32_t)popc32(G.y & 0xffu & ((1u << slot) - 1u));
+      if (G.y & 0xff000000u) stack[sp++] = G;
+      uint32_t cb, pb, im;
+      const uint32_t hm = intersect_node8(bvh.nodes, node, r, &cb, &pb, &im);
+      if (STATS) cnt->nodes++;
+      G.x = cb; G.y = (hm & 0xff000000u) | im;
+      T.x = pb; T.y = hm & 0x00ffffffu;
+    } else {
+      T = G;
+      G.x = 0; G.y = 0;
+    }
+    while (T.y) {
+      const int b = ffs32(T.y) - 1;
+      T.y &= T.y - 1u;
+      const uint32_t prim = T.x + (uint32_t)b;
+      if (in_blas) {
+        const F4 a = ld_f4(bvh.tris + 3ull * prim), bb = ld_f4(bvh.tris + 3ull * prim + 1), c = ld_f4(bvh.tris + 3ull * prim + 2);
+        if (STATS) cnt->tris++;
+        if (woop_hit(r.org, r.sh, r.tmin, r.tmax, v3(a.x, a.y, a.z), v3(bb.x, bb.y, bb.z), v3(c.x, c.y, c.z))) return true;
+      } else {
+        // instance leaf: save the TLAS continuation, switch to object space
+        if (T.y) stack[sp++] = T;
+        if (G.y & 0xff000000u) stack[sp++] = G;
+        U2 s; s.x = kSentinel; s.y = 0;
+        stack[sp++] = s;
+        const F4 r0 = ld_f4(bvh.insts + 4ull * prim), r1 = ld_f4(bvh.insts + 4ull * prim + 1), r2 = ld_f4(bvh.insts + 4ull * prim + 2);
+        const F4 r3 = ld_f4(bvh.insts + 4ull * prim + 3);
+        const float m[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
+        if (STATS) cnt->insts++;
+        ray_setup(r, xf_point(m, org), xf_vector(m, dir), tmin, tmax);
+        in_blas = true;
+        G.x = as_uint(r3.x);
+        G.y = (1u << 24) | 1u;
+        T.y = 0;
+      }
+    }
+    if ((G.y & 0xff000000u) == 0u) {
+      while (true) {
+        if (sp == 0) return false;
+        G = stack[--sp];
+        if (G.x == kSentinel && G.y == 0u) {
+          ray_setup(r, org, dir, tmin, tmax);
+          in_blas = false;
+          continue;
+        }
+        break;
+      }
+    }
+  }
+}
+
+}  // namespace aob

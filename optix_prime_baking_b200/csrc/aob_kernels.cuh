@@ -1,0 +1,561 @@
+// aob_kernels.cuh — every __global__ kernel of libaobake.so (sm_100a).
+//   build   : world triangles + boxes, centroid bounds, Morton keys, LBVH hierarchy/refit,
+//             8-wide collapse, leaf-order gather
+//   sample  : triangle areas, fixed-shape area sums, per-triangle counts, placement
+//   trace   : explicit-ray any-hit, ray dump, fused raygen+traverse+accumulate (two variants)
+//   filter  : area-weighted vertex map, least-squares (matrix-free PCG) pieces
+#pragma once
+#include <cuda_runtime.h>
+#include "aob_bvh.cuh"
+
+namespace aob {
+
+struct Xf12 {
+  float m[12];
+};
+
+// ---------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int float_to_ordered(float f) {
+  int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ordered_to_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+// largest i in [0, n) with a[i] <= v  (a non-decreasing, a[0] <= v)
+template <typename T>
+__device__ __forceinline__ uint64_t upper_slot(const T* __restrict__ a, uint64_t n, T v) {
+  uint64_t lo = 0, hi = n;  // invariant: a[lo] <= v, (hi == n or a[hi] > v)
+  while (hi - lo > 1) {
+    uint64_t mid = (lo + hi) >> 1;
+    if (a[mid] <= v) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// ---------------------------------------------------------------------------------------
+// BVH build
+// ---------------------------------------------------------------------------------------
+// One thread per triangle: (optionally) transform to world space with the exact fp32 formula
+// (aob::xf_point), write the 3 x float4 soup record and the primitive box.
+__global__ void k_make_tris(const float* __restrict__ verts, const uint32_t* __restrict__ tris, uint32_t nT,
+                            Xf12 xf, int identity, uint32_t out_offset, F4* __restrict__ soup,
+                            F4* __restrict__ plo, F4* __restrict__ phi) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nT) return;
+  V3 w[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const uint32_t vi = tris[3ull * t + k];
+    V3 p = v3(verts[3ull * vi], verts[3ull * vi + 1], verts[3ull * vi + 2]);
+    w[k] = identity ? p : xf_point(xf.m, p);
+  }
+  const uint32_t o = out_offset + t;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    F4 f; f.x = w[k].x; f.y = w[k].y; f.z = w[k].z; f.w = __uint_as_float(o);
+    soup[3ull * o + k] = f;
+  }
+  F4 lo, hi;
+  lo.x = fminf(w[0].x, fminf(w[1].x, w[2].x)); lo.y = fminf(w[0].y, fminf(w[1].y, w[2].y)); lo.z = fminf(w[0].z, fminf(w[1].z, w[2].z)); lo.w = 0.f;
+  hi.x = fmaxf(w[0].x, fmaxf(w[1].x, w[2].x)); hi.y = fmaxf(w[0].y, fmaxf(w[1].y, w[2].y)); hi.z = fmaxf(w[0].z, fmaxf(w[1].z, w[2].z)); hi.w = 0.f;
+  plo[o] = lo;
+  phi[o] = hi;
+}
+
+__global__ void k_init_bounds(int* b6) {
+  if (threadIdx.x < 3) b6[threadIdx.x] = 0x7fffffff;
+  else if (threadIdx.x < 6) b6[threadIdx.x] = (int)0x80000000;
+}
+// centroid bounds + full box bounds (b6 = centroid min/max, f6 = box min/max), ordered-int atomics
+__global__ void k_bounds(const F4* __restrict__ plo, const F4* __restrict__ phi, uint32_t n, int* b6, int* f6) {
+  float cmin[3] = {3.0e38f, 3.0e38f, 3.0e38f}, cmax[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+  float fmin_[3] = {3.0e38f, 3.0e38f, 3.0e38f}, fmax_[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const F4 lo = plo[i], hi = phi[i];
+    const float c[3] = {0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z)};
+    const float l[3] = {lo.x, lo.y, lo.z}, h[3] = {hi.x, hi.y, hi.z};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      cmin[k] = fminf(cmin[k], c[k]); cmax[k] = fmaxf(cmax[k], c[k]);
+      fmin_[k] = fminf(fmin_[k], l[k]); fmax_[k] = fmaxf(fmax_[k], h[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    for (int o = 16; o > 0; o >>= 1) {
+      cmin[k] = fminf(cmin[k], __shfl_xor_sync(0xffffffffu, cmin[k], o));
+      cmax[k] = fmaxf(cmax[k], __shfl_xor_sync(0xffffffffu, cmax[k], o));
+      fmin_[k] = fminf(fmin_[k], __shfl_xor_sync(0xffffffffu, fmin_[k], o));
+      fmax_[k] = fmaxf(fmax_[k], __shfl_xor_sync(0xffffffffu, fmax_[k], o));
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      atomicMin(&b6[k], float_to_ordered(cmin[k]));
+      atomicMax(&b6[3 + k], float_to_ordered(cmax[k]));
+      atomicMin(&f6[k], float_to_ordered(fmin_[k]));
+      atomicMax(&f6[3 + k], float_to_ordered(fmax_[k]));
+    }
+  }
+}
+__global__ void k_decode_bounds(const int* f6, float* out6) {
+  if (threadIdx.x < 6) out6[threadIdx.x] = ordered_to_float(f6[threadIdx.x]);
+}
+__global__ void k_morton(const F4* __restrict__ plo, const F4* __restrict__ phi, uint32_t n, const int* __restrict__ b6,
+                         uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const V3 cmin = v3(ordered_to_float(b6[0]), ordered_to_float(b6[1]), ordered_to_float(b6[2]));
+  const V3 cmax = v3(ordered_to_float(b6[3]), ordered_to_float(b6[4]), ordered_to_float(b6[5]));
+  const V3 cinv = v3(cmax.x > cmin.x ? 1.0f / (cmax.x - cmin.x) : 0.f, cmax.y > cmin.y ? 1.0f / (cmax.y - cmin.y) : 0.f,
+                     cmax.z > cmin.z ? 1.0f / (cmax.z - cmin.z) : 0.f);
+  keys[i] = morton63(plo[i], phi[i], cmin, cinv);
+  vals[i] = i;
+}
+__global__ void k_hierarchy(Lbvh L) { lbvh_hierarchy_body(blockIdx.x * blockDim.x + threadIdx.x, L); }
+__global__ void k_refit(Lbvh L) { lbvh_refit_body(blockIdx.x * blockDim.x + threadIdx.x, L); }
+__global__ void k_collapse(CollapseArgs A, uint32_t lb, uint32_t le) {
+  const uint32_t w = lb + blockIdx.x * blockDim.x + threadIdx.x;
+  if (w < le) collapse_body(w, A);
+}
+__global__ void k_set_u32(uint32_t* p, uint32_t v) { *p = v; }
+__global__ void k_gather_tris(const F4* __restrict__ soup, const uint32_t* __restrict__ leaf_prims, uint32_t n,
+                              uint32_t soup_offset, F4* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t s = 3ull * (soup_offset + leaf_prims[i]);
+  out[3ull * i] = soup[s];
+  out[3ull * i + 1] = soup[s + 1];
+  out[3ull * i + 2] = soup[s + 2];
+}
+// empty-tree root: no children hit, ever
+__global__ void k_empty_node(Node8* nd) {
+  Node8 n;
+  memset(&n, 0, sizeof(n));
+  for (int k = 0; k < 8; k++) { n.qlox[k] = n.qloy[k] = n.qloz[k] = 255; }
+  *nd = n;
+}
+
+// ---------------------------------------------------------------------------------------
+// Sampling (bake_sample.cpp)
+// ---------------------------------------------------------------------------------------
+struct InstDesc {
+  float xf[12];
+  float inv[12];
+  const float* verts;     // packed xyz
+  const float* normals;   // packed xyz or null
+  const uint32_t* tris;
+  uint64_t tri_begin;     // offset of this instance's triangles in the flattened element space
+  uint64_t num_tris;
+  uint64_t block_begin;   // offset of its 1024-element blocks
+  uint64_t sample_begin;  // offset of its samples
+  uint64_t num_samples;   // N_i
+  uint32_t seed;          // instance seed (= instance index, decision #10)
+  uint32_t pad;
+};
+
+__device__ __forceinline__ uint32_t find_instance(const InstDesc* __restrict__ inst, uint32_t n_inst, uint64_t e) {
+  uint32_t lo = 0, hi = n_inst;
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (inst[mid].tri_begin <= e) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+__device__ __forceinline__ void load_tri_obj(const InstDesc& I, uint64_t t, V3* p, uint32_t* idx) {
+  idx[0] = I.tris[3 * t]; idx[1] = I.tris[3 * t + 1]; idx[2] = I.tris[3 * t + 2];
+#pragma unroll
+  for (int k = 0; k < 3; k++) p[k] = v3(I.verts[3ull * idx[k]], I.verts[3ull * idx[k] + 1], I.verts[3ull * idx[k] + 2]);
+}
+
+__global__ void k_tri_areas(const InstDesc* __restrict__ inst, uint32_t n_inst, uint64_t total_e, double* __restrict__ area) {
+  const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total_e) return;
+  const InstDesc& I = inst[find_instance(inst, n_inst, e)];
+  V3 p[3];
+  uint32_t idx[3];
+  load_tri_obj(I, e - I.tri_begin, p, idx);
+  area[e] = tri_area(xf_point(I.xf, p[0]), xf_point(I.xf, p[1]), xf_point(I.xf, p[2]));
+}
+// fixed-shape sum, level 1: one thread per 1024-element block, sequential (decision #3)
+__global__ void k_block_sums(const InstDesc* __restrict__ inst, uint32_t n_inst, uint64_t total_blocks,
+                             const double* __restrict__ area, double* __restrict__ bsum) {
+  const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= total_blocks) return;
+  uint32_t lo = 0, hi = n_inst;
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (inst[mid].block_begin <= b) lo = mid; else hi = mid;
+  }
+  const InstDesc& I = inst[lo];
+  const uint64_t j = b - I.block_begin;
+  const uint64_t s = j * 1024, e = min(I.num_tris, s + 1024);
+  double acc = 0.0;
+  for (uint64_t i = s; i < e; i++) acc = ex::dadd(acc, area[I.tri_begin + i]);
+  bsum[b] = acc;
+}
+// level 2: one thread per instance, sequential over its block sums
+__global__ void k_inst_totals(const InstDesc* __restrict__ inst, uint32_t n_inst, const double* __restrict__ bsum,
+                              double* __restrict__ total) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_inst) return;
+  const uint64_t nb = (inst[i].num_tris + 1023) / 1024;
+  double acc = 0.0;
+  for (uint64_t b = 0; b < nb; b++) acc = ex::dadd(acc, bsum[inst[i].block_begin + b]);
+  total[i] = acc;
+}
+__global__ void k_tri_counts(const InstDesc* __restrict__ inst, uint32_t n_inst, uint64_t total_e, const double* __restrict__ area,
+                             const double* __restrict__ total, uint64_t min_per_tri, uint64_t* __restrict__ counts) {
+  const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total_e) return;
+  const uint32_t ii = find_instance(inst, n_inst, e);
+  const InstDesc& I = inst[ii];
+  const uint64_t Na = I.num_samples - min_per_tri * I.num_tris;
+  const double T = total[ii];
+  uint64_t c = min_per_tri;
+  if (Na > 0 && T > 0.0) c += (uint64_t)ex::ddiv(ex::dmul((double)Na, area[e]), T);
+  counts[e] = c;
+}
+// per instance: leftover L_i = N_i - assigned_i; status[0] set to 1 if negative.
+__global__ void k_inst_leftover(const InstDesc* __restrict__ inst, uint32_t n_inst, const uint64_t* __restrict__ offs,
+                                const uint64_t* __restrict__ counts, long long* __restrict__ leftover, int* status) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_inst) return;
+  const InstDesc& I = inst[i];
+  if (I.num_tris == 0) { leftover[i] = 0; if (I.num_samples) atomicExch(status, 2); return; }
+  const uint64_t e1 = I.tri_begin + I.num_tris - 1;
+  const uint64_t assigned = offs[e1] + counts[e1] - offs[I.tri_begin];
+  const long long L = (long long)I.num_samples - (long long)assigned;
+  leftover[i] = L;
+  if (L < 0) atomicExch(status, 1);
+}
+// final per-triangle sample offsets: the leftover sweep adds +1 to triangles 0,1,2,... (wrapping)
+__global__ void k_final_offsets(const InstDesc* __restrict__ inst, uint32_t n_inst, uint64_t total_e, const uint64_t* __restrict__ offs,
+                                const uint64_t* __restrict__ counts, const long long* __restrict__ leftover,
+                                uint64_t* __restrict__ final_off, uint32_t* __restrict__ final_cnt, uint64_t total_samples) {
+  const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e == total_e) final_off[e] = total_samples;
+  if (e >= total_e) return;
+  const uint32_t ii = find_instance(inst, n_inst, e);
+  const InstDesc& I = inst[ii];
+  const uint64_t t = e - I.tri_begin;
+  const uint64_t L = (uint64_t)max(0ll, leftover[ii]);
+  const uint64_t per = L / I.num_tris, rem = L % I.num_tris;
+  final_off[e] = I.sample_begin + (offs[e] - offs[I.tri_begin]) + t * per + min(t, rem);
+  final_cnt[e] = (uint32_t)(counts[e] + per + (t < rem ? 1 : 0));
+}
+// one thread per sample (bake_sample.cpp sample_triangle)
+__global__ void k_place_samples(const InstDesc* __restrict__ inst, uint32_t n_inst, uint64_t total_e,
+                                const uint64_t* __restrict__ final_off, const uint32_t* __restrict__ final_cnt,
+                                const double* __restrict__ area, uint64_t total_samples, float* __restrict__ pos,
+                                float* __restrict__ nrm, float* __restrict__ fnrm, AoSampleInfo* __restrict__ info) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total_samples) return;
+  const uint64_t e = upper_slot<uint64_t>(final_off, total_e, g);
+  const InstDesc& I = inst[find_instance(inst, n_inst, e)];
+  const uint64_t t = e - I.tri_begin;
+  const uint32_t k = (uint32_t)(g - final_off[e]);
+  const uint32_t c = final_cnt[e];
+  V3 p[3];
+  uint32_t idx[3];
+  load_tri_obj(I, t, p, idx);
+  const V3 fn = normalize(cross(sub(p[1], p[0]), sub(p[2], p[0])));
+  V3 n0 = fn, n1 = fn, n2 = fn;
+  if (I.normals) {
+    n0 = v3(I.normals[3ull * idx[0]], I.normals[3ull * idx[0] + 1], I.normals[3ull * idx[0] + 2]);
+    n1 = v3(I.normals[3ull * idx[1]], I.normals[3ull * idx[1] + 1], I.normals[3ull * idx[1] + 2]);
+    n2 = v3(I.normals[3ull * idx[2]], I.normals[3ull * idx[2] + 1], I.normals[3ull * idx[2] + 2]);
+    if (dot(n0, fn) < 0.0f) n0 = neg(n0);
+    if (dot(n1, fn) < 0.0f) n1 = neg(n1);
+    if (dot(n2, fn) < 0.0f) n2 = neg(n2);
+  }
+  const V3 fnw = normalize(xf_normal(I.inv, fn));
+  uint32_t seed = tea<4>(I.seed, (uint32_t)t);
+  const float ox = rnd(seed), oy = rnd(seed);
+  float r1 = ex::add(ox, halton(k + 1, 2)); r1 = ex::sub(r1, floorf(r1));
+  float r2 = ex::add(oy, halton(k + 1, 3)); r2 = ex::sub(r2, floorf(r2));
+  const float s = ex::sqrt(r1);
+  const float b0 = ex::sub(1.0f, s), b1 = ex::mul(r2, s), b2 = ex::sub(ex::sub(1.0f, b0), b1);
+  const V3 po = v3(ex::add(ex::add(ex::mul(b0, p[0].x), ex::mul(b1, p[1].x)), ex::mul(b2, p[2].x)),
+                   ex::add(ex::add(ex::mul(b0, p[0].y), ex::mul(b1, p[1].y)), ex::mul(b2, p[2].y)),
+                   ex::add(ex::add(ex::mul(b0, p[0].z), ex::mul(b1, p[1].z)), ex::mul(b2, p[2].z)));
+  const V3 pw = xf_point(I.xf, po);
+  const V3 no = v3(ex::add(ex::add(ex::mul(b0, n0.x), ex::mul(b1, n1.x)), ex::mul(b2, n2.x)),
+                   ex::add(ex::add(ex::mul(b0, n0.y), ex::mul(b1, n1.y)), ex::mul(b2, n2.y)),
+                   ex::add(ex::add(ex::mul(b0, n0.z), ex::mul(b1, n1.z)), ex::mul(b2, n2.z)));
+  const V3 nw = normalize(xf_normal(I.inv, no));
+  pos[3 * g] = pw.x; pos[3 * g + 1] = pw.y; pos[3 * g + 2] = pw.z;
+  nrm[3 * g] = nw.x; nrm[3 * g + 1] = nw.y; nrm[3 * g + 2] = nw.z;
+  fnrm[3 * g] = fnw.x; fnrm[3 * g + 1] = fnw.y; fnrm[3 * g + 2] = fnw.z;
+  AoSampleInfo si;
+  si.tri_idx = (uint32_t)t;
+  si.bary[0] = b0; si.bary[1] = b1; si.bary[2] = b2;
+  si.dA = (float)ex::ddiv(area[e], (double)c);
+  info[g] = si;
+}
+
+// ---------------------------------------------------------------------------------------
+// Trace
+// ---------------------------------------------------------------------------------------
+__global__ void k_trace_rays(BvhView bvh, const float* __restrict__ rays, uint64_t n, uint8_t* __restrict__ hit) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 a = reinterpret_cast<const float4*>(rays)[2 * i], b = reinterpret_cast<const float4*>(rays)[2 * i + 1];
+  U2 stack[kStackSize];
+  hit[i] = trace_any_hit<false>(bvh, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), a.w, b.w, stack, nullptr) ? 1 : 0;
+}
+
+struct SampleView {
+  const float* pos;
+  const float* nrm;
+  const float* fnrm;
+};
+
+__global__ void k_dump_rays(SampleView S, uint64_t begin, uint64_t end, int q, float offset, float maxdist, float* __restrict__ out) {
+  const uint64_t q2 = (uint64_t)q * q;
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (end - begin) * q2) return;
+  const uint64_t g = begin + i / q2;
+  const uint32_t pass = (uint32_t)(i % q2);
+  const V3 p = v3(S.pos[3 * g], S.pos[3 * g + 1], S.pos[3 * g + 2]), n = v3(S.nrm[3 * g], S.nrm[3 * g + 1], S.nrm[3 * g + 2]),
+           fn = v3(S.fnrm[3 * g], S.fnrm[3 * g + 1], S.fnrm[3 * g + 2]);
+  const Onb onb = make_onb(n);
+  const V3 o = ao_ray_origin(p, n, offset);
+  const V3 d = ao_ray_dir((uint32_t)g, pass, q, n, fn, onb);
+  float4* r = reinterpret_cast<float4*>(out) + 2 * i;
+  r[0] = make_float4(o.x, o.y, o.z, 0.0f);
+  r[1] = make_float4(d.x, d.y, d.z, maxdist);
+}
+
+// Variant 1 (simple): one warp per (32-sample block, strata chunk); lane = sample; each lane
+// walks its strata sequentially with a private local-memory stack.
+template <bool STATS>
+__global__ void __launch_bounds__(256) k_ao_simple(BvhView bvh, SampleView S, uint64_t begin, uint64_t end, int q, float offset,
+                                                   float maxdist, uint32_t n_chunks, uint32_t* __restrict__ hits,
+                                                   unsigned long long* __restrict__ stats) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t n_blocks = (end - begin + 31) / 32;
+  if (warp >= n_blocks * n_chunks) return;
+  const uint64_t sblock = warp / n_chunks;
+  const uint32_t chunk = (uint32_t)(warp % n_chunks);
+  const uint64_t g = begin + sblock * 32 + lane;
+  if (g >= end) return;
+  const uint32_t q2 = (uint32_t)(q * q);
+  const uint32_t p0 = (uint32_t)(((uint64_t)chunk * q2) / n_chunks), p1 = (uint32_t)(((uint64_t)(chunk + 1) * q2) / n_chunks);
+  const V3 p = v3(S.pos[3 * g], S.pos[3 * g + 1], S.pos[3 * g + 2]), n = v3(S.nrm[3 * g], S.nrm[3 * g + 1], S.nrm[3 * g + 2]),
+           fn = v3(S.fnrm[3 * g], S.fnrm[3 * g + 1], S.fnrm[3 * g + 2]);
+  const Onb onb = make_onb(n);
+  const V3 o = ao_ray_origin(p, n, offset);
+  U2 stack[kStackSize];
+  TraceCounters cnt = {0, 0, 0};
+  uint32_t h = 0;
+  for (uint32_t pass = p0; pass < p1; pass++) {
+    const V3 d = ao_ray_dir((uint32_t)g, pass, q, n, fn, onb);
+    h += trace_any_hit<STATS>(bvh, o, d, 0.0f, maxdist, stack, &cnt) ? 1u : 0u;
+  }
+  if (n_chunks > 1) atomicAdd(&hits[g - begin], h);
+  else hits[g - begin] = h;
+  if (STATS) {
+    atomicAdd(&stats[0], (unsigned long long)cnt.nodes);
+    atomicAdd(&stats[1], (unsigned long long)cnt.tris);
+    atomicAdd(&stats[2], (unsigned long long)cnt.insts);
+  }
+}
+
+__global__ void k_ao_finalize(const uint32_t* __restrict__ hits, uint64_t n, float denom, float* __restrict__ ao) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  ao[i] = ex::sub(1.0f, ex::div((float)hits[i], denom));
+}
+
+// ---------------------------------------------------------------------------------------
+// Vertex maps
+// ---------------------------------------------------------------------------------------
+// bake_filter.cpp filter_mesh: scatter ao*bary*dA and bary*dA (fp64 atomics), then divide.
+__global__ void k_area_scatter(const AoSampleInfo* __restrict__ info, const float* __restrict__ ao, uint64_t begin, uint64_t count,
+                               const uint32_t* __restrict__ tris, double* __restrict__ num, double* __restrict__ wgt) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const AoSampleInfo si = info[begin + i];
+  const double dA = si.dA, val = (double)ao[begin + i] * dA;
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    const uint32_t v = tris[3ull * si.tri_idx + c];
+    atomicAdd(&num[v], (double)si.bary[c] * val);
+    atomicAdd(&wgt[v], (double)si.bary[c] * dA);
+  }
+}
+__global__ void k_area_final(const double* __restrict__ num, const double* __restrict__ wgt, uint64_t nV, float* __restrict__ out) {
+  const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nV) return;
+  out[v] = wgt[v] > 0.0 ? (float)(num[v] / wgt[v]) : 0.0f;
+}
+
+// ---- least squares (bake_filter_least_squares.cpp; Kavan et al. 2011) ---------------------
+// sampled mass blocks per triangle (6 unique entries) and rhs
+__global__ void k_ls_mass(const AoSampleInfo* __restrict__ info, const float* __restrict__ ao, uint64_t begin, uint64_t count,
+                          const uint32_t* __restrict__ tris, double* __restrict__ Mt, double* __restrict__ rhs) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const AoSampleInfo si = info[begin + i];
+  const double dA = si.dA, a = ao[begin + i], b0 = si.bary[0], b1 = si.bary[1], b2 = si.bary[2];
+  double* M = Mt + 6ull * si.tri_idx;
+  atomicAdd(&M[0], dA * b0 * b0); atomicAdd(&M[1], dA * b0 * b1); atomicAdd(&M[2], dA * b0 * b2);
+  atomicAdd(&M[3], dA * b1 * b1); atomicAdd(&M[4], dA * b1 * b2); atomicAdd(&M[5], dA * b2 * b2);
+  const uint32_t* idx = tris + 3ull * si.tri_idx;
+  atomicAdd(&rhs[idx[0]], dA * a * b0); atomicAdd(&rhs[idx[1]], dA * a * b1); atomicAdd(&rhs[idx[2]], dA * a * b2);
+}
+// half-edge keys: (min(a,b) << 32 | max(a,b)), value = 3*tri + e; degenerate edges get key ~0
+__global__ void k_ls_halfedges(const uint32_t* __restrict__ tris, uint64_t nT, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 3 * nT) return;
+  const uint64_t t = i / 3;
+  const uint32_t e = (uint32_t)(i % 3);
+  const uint32_t a = tris[3 * t + e], b = tris[3 * t + (e + 1) % 3];
+  keys[i] = (a == b) ? ~0ull : (((uint64_t)min(a, b) << 32) | max(a, b));
+  vals[i] = (uint32_t)i;
+}
+struct LsEdge {
+  uint32_t i, j, p, q;
+  double c[4];
+};
+// one thread per sorted half-edge; the first of a run of >= 2 equal keys emits an interior edge
+__global__ void k_ls_edges(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t nH,
+                           const uint32_t* __restrict__ tris, const float* __restrict__ verts, Xf12 xf,
+                           LsEdge* __restrict__ edges, uint32_t* __restrict__ edge_count) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k + 1 >= nH) return;
+  const uint64_t key = keys[k];
+  if (key == ~0ull) return;
+  if (k > 0 && keys[k - 1] == key) return;
+  if (keys[k + 1] != key) return;
+  LsEdge E;
+  E.i = (uint32_t)(key >> 32);
+  E.j = (uint32_t)(key & 0xffffffffu);
+  const uint32_t h0 = vals[k], h1 = vals[k + 1];
+  E.p = tris[3ull * (h0 / 3) + (h0 % 3 + 2) % 3];
+  E.q = tris[3ull * (h1 / 3) + (h1 % 3 + 2) % 3];
+  auto W = [&](uint32_t v) { return xf_point(xf.m, v3(verts[3ull * v], verts[3ull * v + 1], verts[3ull * v + 2])); };
+  const V3 pi = W(E.i), pj = W(E.j), pp = W(E.p), pq = W(E.q);
+  const double ex_ = (double)pj.x - pi.x, ey_ = (double)pj.y - pi.y, ez_ = (double)pj.z - pi.z;
+  const double L2 = ex_ * ex_ + ey_ * ey_ + ez_ * ez_;
+  if (!(L2 > 0.0)) return;
+  double s[2], h[2], A[2];
+  const V3 opp[2] = {pp, pq};
+#pragma unroll
+  for (int m = 0; m < 2; m++) {
+    const double ox = (double)opp[m].x - pi.x, oy = (double)opp[m].y - pi.y, oz = (double)opp[m].z - pi.z;
+    s[m] = (ox * ex_ + oy * ey_ + oz * ez_) / L2;
+    const double rx = ox - s[m] * ex_, ry = oy - s[m] * ey_, rz = oz - s[m] * ez_;
+    h[m] = sqrt(rx * rx + ry * ry + rz * rz);
+    A[m] = 0.5 * sqrt(L2) * h[m];
+  }
+  if (!(h[0] > 0.0 && h[1] > 0.0)) return;
+  const double w = A[0] + A[1];
+  E.c[0] = w * ((1.0 - s[0]) / h[0] + (1.0 - s[1]) / h[1]);
+  E.c[1] = w * (s[0] / h[0] + s[1] / h[1]);
+  E.c[2] = w * (-1.0 / h[0]);
+  E.c[3] = w * (-1.0 / h[1]);
+  edges[atomicAdd(edge_count, 1u)] = E;
+}
+__global__ void k_ls_diag(const uint32_t* __restrict__ tris, uint64_t nT, const double* __restrict__ Mt, const LsEdge* __restrict__ edges,
+                          uint32_t nE, double w, double* __restrict__ diag) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nT) {
+    atomicAdd(&diag[tris[3 * i]], Mt[6 * i]);
+    atomicAdd(&diag[tris[3 * i + 1]], Mt[6 * i + 3]);
+    atomicAdd(&diag[tris[3 * i + 2]], Mt[6 * i + 5]);
+  }
+  if (i < nE) {
+    const LsEdge E = edges[i];
+    atomicAdd(&diag[E.i], w * E.c[0] * E.c[0]); atomicAdd(&diag[E.j], w * E.c[1] * E.c[1]);
+    atomicAdd(&diag[E.p], w * E.c[2] * E.c[2]); atomicAdd(&diag[E.q], w * E.c[3] * E.c[3]);
+  }
+}
+// rows with zero diagonal: diag = 1, rhs = 0 (decision #7)
+__global__ void k_ls_fix(double* __restrict__ diag, double* __restrict__ rhs, uint8_t* __restrict__ fixed, uint64_t nV) {
+  const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nV) return;
+  const bool f = !(diag[v] > 0.0);
+  fixed[v] = f ? 1 : 0;
+  if (f) { diag[v] = 1.0; rhs[v] = 0.0; }
+}
+// y += (M + w R) x   (y zeroed by the caller); one thread per triangle and per edge
+__global__ void k_ls_apply(const uint32_t* __restrict__ tris, uint64_t nT, const double* __restrict__ Mt, const LsEdge* __restrict__ edges,
+                           uint32_t nE, double w, const double* __restrict__ x, double* __restrict__ y) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nT) {
+    const uint32_t a = tris[3 * i], b = tris[3 * i + 1], c = tris[3 * i + 2];
+    const double* M = Mt + 6 * i;
+    const double m0 = M[0], m1 = M[1], m2 = M[2], m3 = M[3], m4 = M[4], m5 = M[5];
+    if (m0 != 0.0 || m3 != 0.0 || m5 != 0.0) {
+      const double x0 = x[a], x1 = x[b], x2 = x[c];
+      atomicAdd(&y[a], m0 * x0 + m1 * x1 + m2 * x2);
+      atomicAdd(&y[b], m1 * x0 + m3 * x1 + m4 * x2);
+      atomicAdd(&y[c], m2 * x0 + m4 * x1 + m5 * x2);
+    }
+  }
+  if (i < nE) {
+    const LsEdge E = edges[i];
+    const double J = E.c[0] * x[E.i] + E.c[1] * x[E.j] + E.c[2] * x[E.p] + E.c[3] * x[E.q];
+    const double wj = w * J;
+    atomicAdd(&y[E.i], wj * E.c[0]); atomicAdd(&y[E.j], wj * E.c[1]);
+    atomicAdd(&y[E.p], wj * E.c[2]); atomicAdd(&y[E.q], wj * E.c[3]);
+  }
+}
+__global__ void k_ls_fix_apply(const uint8_t* __restrict__ fixed, const double* __restrict__ p, double* __restrict__ Ap, uint64_t nV) {
+  const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < nV && fixed[v]) Ap[v] = p[v];
+}
+// out[slot] += sum a[i]*b[i]  (block reduce + one fp64 atomic per block)
+__global__ void k_dot(const double* __restrict__ a, const double* __restrict__ b, uint64_t n, double* __restrict__ out) {
+  __shared__ double sh[32];
+  double acc = 0.0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) acc += a[i] * b[i];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    acc = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (threadIdx.x == 0) atomicAdd(out, acc);
+  }
+}
+// z = r / diag ; p = z (init) ; scal[0] += r.z
+__global__ void k_ls_init(const double* __restrict__ rhs, const double* __restrict__ diag, double* __restrict__ r, double* __restrict__ z,
+                          double* __restrict__ p, double* __restrict__ x, uint64_t nV) {
+  const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nV) return;
+  x[v] = 0.0;
+  r[v] = rhs[v];
+  z[v] = rhs[v] / diag[v];
+  p[v] = z[v];
+}
+// x += alpha p ; r -= alpha Ap ; z = r/diag     (alpha = scal[rz]/scal[pAp] read on device)
+__global__ void k_ls_update(const double* __restrict__ scal, int i_rz, int i_pap, const double* __restrict__ p, const double* __restrict__ Ap,
+                            const double* __restrict__ diag, double* __restrict__ x, double* __restrict__ r, double* __restrict__ z, uint64_t nV) {
+  const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nV) return;
+  const double alpha = scal[i_rz] / scal[i_pap];
+  x[v] += alpha * p[v];
+  const double rv = r[v] - alpha * Ap[v];
+  r[v] = rv;
+  z[v] = rv / diag[v];
+}
+// p = z + beta p   (beta = scal[rz_new]/scal[rz_old])
+__global__ void k_ls_dir(const double* __restrict__ scal, int i_new, int i_old, const double* __restrict__ z, double* __restrict__ p, uint64_t nV) {
+  const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nV) return;
+  const double beta = scal[i_new] / scal[i_old];
+  p[v] = z[v] + beta * p[v];
+}
+__global__ void k_d2f(const double* __restrict__ x, float* __restrict__ out, uint64_t n) {
+  const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < n) out[v] = (float)x[v];
+}
+
+}  // namespace aob

@@ -1,0 +1,234 @@
+// aob_math.cuh — exactly-rounded fp32/fp64 building blocks shared by every kernel.
+//
+// Every operation that feeds a bit-exact parity check (sample placement, ray generation,
+// the watertight triangle test, instance transforms) goes through ex::mul/add/sub/div/sqrt,
+// which map to __fmul_rn/__fadd_rn/... on the device (never contracted into FMAs by nvcc)
+// and to plain operators on the host (compiled with -ffp-contract=off).  One IEEE rounding
+// per operation, evaluated in the order written — the arithmetic contract of BASELINE.md §4.
+//
+// The header also compiles under plain g++ (AOB_HOST_EMU) so the host-emulation tests can
+// run the same code on CPU.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define AOB_HD __host__ __device__ __forceinline__
+#define AOB_D __device__ __forceinline__
+#else
+#define AOB_HD inline
+#define AOB_D inline
+#endif
+
+namespace aob {
+
+struct V3 {
+  float x, y, z;
+};
+AOB_HD V3 v3(float x, float y, float z) {
+  V3 r;
+  r.x = x; r.y = y; r.z = z;
+  return r;
+}
+
+namespace ex {
+#if defined(__CUDA_ARCH__)
+AOB_HD float mul(float a, float b) { return __fmul_rn(a, b); }
+AOB_HD float add(float a, float b) { return __fadd_rn(a, b); }
+AOB_HD float sub(float a, float b) { return __fsub_rn(a, b); }
+AOB_HD float div(float a, float b) { return __fdiv_rn(a, b); }
+AOB_HD float sqrt(float a) { return __fsqrt_rn(a); }
+AOB_HD double dmul(double a, double b) { return __dmul_rn(a, b); }
+AOB_HD double dadd(double a, double b) { return __dadd_rn(a, b); }
+AOB_HD double dsub(double a, double b) { return __dsub_rn(a, b); }
+AOB_HD double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+AOB_HD double dsqrt(double a) { return __dsqrt_rn(a); }
+#else
+AOB_HD float mul(float a, float b) { return a * b; }
+AOB_HD float add(float a, float b) { return a + b; }
+AOB_HD float sub(float a, float b) { return a - b; }
+AOB_HD float div(float a, float b) { return a / b; }
+AOB_HD float sqrt(float a) { return ::sqrtf(a); }
+AOB_HD double dmul(double a, double b) { return a * b; }
+AOB_HD double dadd(double a, double b) { return a + b; }
+AOB_HD double dsub(double a, double b) { return a - b; }
+AOB_HD double ddiv(double a, double b) { return a / b; }
+AOB_HD double dsqrt(double a) { return ::sqrt(a); }
+#endif
+// (a*b + c*d) + e*f
+AOB_HD float dot3(float a, float b, float c, float d, float e, float f) {
+  return add(add(mul(a, b), mul(c, d)), mul(e, f));
+}
+}  // namespace ex
+
+AOB_HD V3 sub(V3 a, V3 b) { return v3(ex::sub(a.x, b.x), ex::sub(a.y, b.y), ex::sub(a.z, b.z)); }
+AOB_HD V3 neg(V3 a) { return v3(-a.x, -a.y, -a.z); }
+AOB_HD float dot(V3 a, V3 b) { return ex::dot3(a.x, b.x, a.y, b.y, a.z, b.z); }
+AOB_HD V3 cross(V3 a, V3 b) {
+  return v3(ex::sub(ex::mul(a.y, b.z), ex::mul(a.z, b.y)), ex::sub(ex::mul(a.z, b.x), ex::mul(a.x, b.z)),
+            ex::sub(ex::mul(a.x, b.y), ex::mul(a.y, b.x)));
+}
+AOB_HD V3 normalize(V3 a) {
+  float len = ex::sqrt(dot(a, a));
+  if (!(len > 0.0f)) return a;
+  return v3(ex::div(a.x, len), ex::div(a.y, len), ex::div(a.z, len));
+}
+AOB_HD float comp(V3 a, int k) { return k == 0 ? a.x : (k == 1 ? a.y : a.z); }
+
+// world = M * (v,1) for a row-major matrix whose first 12 floats are the 3x4 affine part.
+AOB_HD V3 xf_point(const float* m, V3 v) {
+  return v3(ex::add(ex::add(ex::add(ex::mul(m[0], v.x), ex::mul(m[1], v.y)), ex::mul(m[2], v.z)), m[3]),
+            ex::add(ex::add(ex::add(ex::mul(m[4], v.x), ex::mul(m[5], v.y)), ex::mul(m[6], v.z)), m[7]),
+            ex::add(ex::add(ex::add(ex::mul(m[8], v.x), ex::mul(m[9], v.y)), ex::mul(m[10], v.z)), m[11]));
+}
+AOB_HD V3 xf_vector(const float* m, V3 d) {
+  return v3(ex::dot3(m[0], d.x, m[1], d.y, m[2], d.z), ex::dot3(m[4], d.x, m[5], d.y, m[6], d.z),
+            ex::dot3(m[8], d.x, m[9], d.y, m[10], d.z));
+}
+// n_world = (inv 3x3)^T * n
+AOB_HD V3 xf_normal(const float* inv, V3 n) {
+  return v3(ex::dot3(inv[0], n.x, inv[4], n.y, inv[8], n.z), ex::dot3(inv[1], n.x, inv[5], n.y, inv[9], n.z),
+            ex::dot3(inv[2], n.x, inv[6], n.y, inv[10], n.z));
+}
+
+// ---- RNG: tea<N>, lcg, rnd of the reference's random.h -----------------
+template <unsigned N>
+AOB_HD uint32_t tea(uint32_t v0, uint32_t v1) {
+  uint32_t s0 = 0;
+#pragma unroll
+  for (unsigned n = 0; n < N; n++) {
+    s0 += 0x9e3779b9u;
+    v0 += ((v1 << 4) + 0xa341316cu) ^ (v1 + s0) ^ ((v1 >> 5) + 0xc8013ea4u);
+    v1 += ((v0 << 4) + 0xad90777du) ^ (v0 + s0) ^ ((v0 >> 5) + 0x7e95761eu);
+  }
+  return v0;
+}
+AOB_HD uint32_t lcg(uint32_t& s) {
+  s = 1664525u * s + 1013904223u;
+  return s & 0x00FFFFFFu;
+}
+AOB_HD float rnd(uint32_t& s) { return ex::div((float)lcg(s), 16777216.0f); }
+
+// radical inverse, fp32 accumulate (bake_sample.cpp; decision #4)
+AOB_HD float halton(uint32_t i, uint32_t base) {
+  const float inv_base = ex::div(1.0f, (float)base);
+  float f = inv_base, r = 0.0f;
+  while (i) {
+    r = ex::add(r, ex::mul(f, (float)(i % base)));
+    i /= base;
+    f = ex::mul(f, inv_base);
+  }
+  return r;
+}
+
+// cos/sin(2*pi*u), u in [0,1): quadrant reduction + fixed polynomials (decision #11).
+AOB_HD void sincos2pi(float u, float* c, float* s) {
+  int qi = (int)floorf(ex::add(ex::mul(4.0f, u), 0.5f));
+  float r = ex::sub(u, ex::mul(0.25f, (float)qi));
+  float th = ex::mul(6.28318548202514648f, r);
+  float t2 = ex::mul(th, th);
+  float sp = ex::add(ex::mul(-1.9515295891e-4f, t2), 8.3321608736e-3f);
+  sp = ex::add(ex::mul(sp, t2), -1.6666654611e-1f);
+  float sn = ex::add(ex::mul(ex::mul(sp, t2), th), th);
+  float cp = ex::add(ex::mul(2.443315711809948e-5f, t2), -1.388731625493765e-3f);
+  cp = ex::add(ex::mul(cp, t2), 4.166664568298827e-2f);
+  float cs = ex::add(ex::mul(ex::mul(cp, t2), t2), ex::sub(1.0f, ex::mul(0.5f, t2)));
+  switch (qi & 3) {
+    case 0: *c = cs; *s = sn; break;
+    case 1: *c = -sn; *s = cs; break;
+    case 2: *c = -cs; *s = -sn; break;
+    default: *c = sn; *s = -cs; break;
+  }
+}
+
+// 0.5*|e0 x e1|: cross in fp32, norm in fp64
+AOB_HD double tri_area(V3 w0, V3 w1, V3 w2) {
+  V3 c = cross(sub(w1, w0), sub(w2, w0));
+  double cx = c.x, cy = c.y, cz = c.z;
+  return ex::dmul(0.5, ex::dsqrt(ex::dadd(ex::dadd(ex::dmul(cx, cx), ex::dmul(cy, cy)), ex::dmul(cz, cz))));
+}
+
+// ---- ray generation (bake_kernels.cu generateRaysKernel) ------------------
+AOB_HD int sqrt_rays(int rays_per_sample) { return (int)(ex::add(ex::sqrt((float)rays_per_sample), 0.5f)); }
+
+struct Onb {
+  V3 t, b;
+};
+AOB_HD Onb make_onb(V3 n) {
+  Onb o;
+  if (fabsf(n.x) > fabsf(n.z)) o.b = v3(-n.y, n.x, 0.0f);
+  else o.b = v3(0.0f, -n.z, n.y);
+  o.b = normalize(o.b);
+  o.t = cross(o.b, n);
+  return o;
+}
+AOB_HD V3 cosine_dir(float u0, float u1, V3 n, const Onb& o) {
+  float r = ex::sqrt(u0), c, s;
+  sincos2pi(u1, &c, &s);
+  float x = ex::mul(r, c), y = ex::mul(r, s);
+  float z = ex::sqrt(fmaxf(0.0f, ex::sub(ex::sub(1.0f, ex::mul(x, x)), ex::mul(y, y))));
+  return v3(ex::add(ex::add(ex::mul(x, o.t.x), ex::mul(y, o.b.x)), ex::mul(z, n.x)),
+            ex::add(ex::add(ex::mul(x, o.t.y), ex::mul(y, o.b.y)), ex::mul(z, n.y)),
+            ex::add(ex::add(ex::mul(x, o.t.z), ex::mul(y, o.b.z)), ex::mul(z, n.z)));
+}
+// direction of stratum `pass` (= px*q+py) of global sample g.
+AOB_HD V3 ao_ray_dir(uint32_t g, uint32_t pass, int q, V3 n, V3 fn, const Onb& onb) {
+  const uint32_t px = pass / (uint32_t)q, py = pass - px * (uint32_t)q;
+  uint32_t seed = tea<2>((pass << 16) | pass, g);
+  float u0 = ex::div(ex::add((float)px, rnd(seed)), (float)q);
+  float u1 = ex::div(ex::add((float)py, rnd(seed)), (float)q);
+  V3 d = v3(0.f, 0.f, 0.f);
+  for (int attempt = 0; attempt < 5; attempt++) {
+    d = cosine_dir(u0, u1, n, onb);
+    if (dot(d, fn) > 0.0f) break;
+    u0 = rnd(seed);
+    u1 = rnd(seed);
+  }
+  return d;
+}
+AOB_HD V3 ao_ray_origin(V3 p, V3 n, float offset) {
+  return v3(ex::add(p.x, ex::mul(offset, n.x)), ex::add(p.y, ex::mul(offset, n.y)), ex::add(p.z, ex::mul(offset, n.z)));
+}
+
+// ---- watertight ray/triangle (Woop, Benthin, Wald 2013), any-hit with (tmin, tmax) --------
+struct Shear {
+  int kx, ky, kz;
+  float Sx, Sy, Sz;
+};
+AOB_HD Shear make_shear(V3 d) {
+  Shear s;
+  float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+  s.kz = (ax > ay) ? ((ax > az) ? 0 : 2) : ((ay > az) ? 1 : 2);
+  s.kx = s.kz + 1; if (s.kx == 3) s.kx = 0;
+  s.ky = s.kx + 1; if (s.ky == 3) s.ky = 0;
+  float dz = comp(d, s.kz);
+  if (dz < 0.0f) { int t = s.kx; s.kx = s.ky; s.ky = t; }
+  s.Sx = ex::div(comp(d, s.kx), dz);
+  s.Sy = ex::div(comp(d, s.ky), dz);
+  s.Sz = ex::div(1.0f, dz);
+  return s;
+}
+AOB_HD bool woop_hit(V3 org, const Shear& s, float tmin, float tmax, V3 p0, V3 p1, V3 p2) {
+  V3 A = sub(p0, org), B = sub(p1, org), C = sub(p2, org);
+  float Akz = comp(A, s.kz), Bkz = comp(B, s.kz), Ckz = comp(C, s.kz);
+  float Ax = ex::sub(comp(A, s.kx), ex::mul(s.Sx, Akz)), Ay = ex::sub(comp(A, s.ky), ex::mul(s.Sy, Akz));
+  float Bx = ex::sub(comp(B, s.kx), ex::mul(s.Sx, Bkz)), By = ex::sub(comp(B, s.ky), ex::mul(s.Sy, Bkz));
+  float Cx = ex::sub(comp(C, s.kx), ex::mul(s.Sx, Ckz)), Cy = ex::sub(comp(C, s.ky), ex::mul(s.Sy, Ckz));
+  float U = ex::sub(ex::mul(Cx, By), ex::mul(Cy, Bx));
+  float V = ex::sub(ex::mul(Ax, Cy), ex::mul(Ay, Cx));
+  float W = ex::sub(ex::mul(Bx, Ay), ex::mul(By, Ax));
+  if (U == 0.0f || V == 0.0f || W == 0.0f) {
+    U = (float)ex::dsub(ex::dmul((double)Cx, (double)By), ex::dmul((double)Cy, (double)Bx));
+    V = (float)ex::dsub(ex::dmul((double)Ax, (double)Cy), ex::dmul((double)Ay, (double)Cx));
+    W = (float)ex::dsub(ex::dmul((double)Bx, (double)Ay), ex::dmul((double)By, (double)Ax));
+  }
+  if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+  float det = ex::add(ex::add(U, V), W);
+  if (det == 0.0f) return false;
+  float Az = ex::mul(s.Sz, Akz), Bz = ex::mul(s.Sz, Bkz), Cz = ex::mul(s.Sz, Ckz);
+  float T = ex::add(ex::add(ex::mul(U, Az), ex::mul(V, Bz)), ex::mul(W, Cz));
+  float t = ex::div(T, det);
+  return (t > tmin) && (t < tmax);
+}
+
+}  // namespace aob

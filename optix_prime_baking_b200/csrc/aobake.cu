@@ -1,0 +1,1005 @@
+// aobake.cu — host orchestrator + C-ABI of libaobake.so (see include/aobake.h).
+//
+// Everything that touches geometry, samples, rays or AO runs in the CUDA kernels of
+// aob_kernels.cuh; this file owns device memory, launch order, CUDA events and the
+// status/last-error convention.  There is no CPU fallback: aobake_create fails without a
+// CUDA device, and every compute entry point requires a live context.
+#include <cuda_runtime.h>
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "aobake.h"
+#include "aob_kernels.cuh"
+
+using namespace aob;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+template <typename T>
+struct DBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DBuf() = default;
+  DBuf(const DBuf&) = delete;
+  DBuf& operator=(const DBuf&) = delete;
+  DBuf(DBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DBuf& operator=(DBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
+  ~DBuf() { release(); }
+  cudaError_t alloc(size_t count) {
+    release();
+    n = count;
+    if (count == 0) return cudaSuccess;
+    return cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T));
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  void swap(DBuf& o) { std::swap(p, o.p); std::swap(n, o.n); }
+};
+
+struct DeviceMesh {
+  uint64_t nV = 0, nT = 0;
+  DBuf<float> verts;    // packed xyz
+  DBuf<float> normals;  // packed xyz or empty
+  DBuf<uint32_t> tris;
+};
+struct HostInstance {
+  float xf[12];
+  float inv[12];
+  uint32_t mesh;
+  uint64_t storage_id;
+};
+
+double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// inverse of the affine part in fp64 by cofactors, rounded to fp32 once (BASELINE.md §4.2;
+// the reference's Matrix4x4::inverse in bake_sample.cpp).  Host code of this file is built with
+// -ffp-contract=off so the result is reproducible.
+void affine_inverse(const float* m, float* inv) {
+  const double a00 = m[0], a01 = m[1], a02 = m[2], t0 = m[3];
+  const double a10 = m[4], a11 = m[5], a12 = m[6], t1 = m[7];
+  const double a20 = m[8], a21 = m[9], a22 = m[10], t2 = m[11];
+  const double c00 = a11 * a22 - a12 * a21, c01 = a02 * a21 - a01 * a22, c02 = a01 * a12 - a02 * a11;
+  const double c10 = a12 * a20 - a10 * a22, c11 = a00 * a22 - a02 * a20, c12 = a02 * a10 - a00 * a12;
+  const double c20 = a10 * a21 - a11 * a20, c21 = a01 * a20 - a00 * a21, c22 = a00 * a11 - a01 * a10;
+  const double det = (a00 * c00 + a01 * c10) + a02 * c20;
+  const double i[9] = {c00 / det, c01 / det, c02 / det, c10 / det, c11 / det, c12 / det, c20 / det, c21 / det, c22 / det};
+  for (int r = 0; r < 3; r++) {
+    inv[4 * r + 0] = (float)i[3 * r + 0];
+    inv[4 * r + 1] = (float)i[3 * r + 1];
+    inv[4 * r + 2] = (float)i[3 * r + 2];
+    inv[4 * r + 3] = (float)(-((i[3 * r + 0] * t0 + i[3 * r + 1] * t1) + i[3 * r + 2] * t2));
+  }
+}
+
+inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
+
+}  // namespace
+
+struct AoBake {
+  AoBakeParams params;
+  int device = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  int sm_count = 148;
+
+  // scene
+  bool have_scene = false;
+  std::vector<DeviceMesh> meshes;          // scene meshes (blockers are only needed for the BVH)
+  std::vector<HostInstance> insts;         // scene instances
+  std::vector<uint64_t> inst_num_verts;
+  DBuf<InstDesc> d_inst;                   // sampling descriptors (refreshed per sample call)
+  DBuf<double> d_tri_area, d_bsum, d_inst_area;
+  std::vector<double> inst_area;           // host copy
+  uint64_t total_tris = 0, total_blocks = 0;
+  bool areas_ready = false;
+
+  // BVH
+  DBuf<Node8> d_nodes;
+  DBuf<F4> d_tris;
+  DBuf<F4> d_insts;
+  uint32_t root = 0;
+  bool two_level = false;
+  AoStats stats{};
+
+  // samples + AO
+  uint64_t num_samples = 0;
+  DBuf<float> d_pos, d_nrm, d_fnrm;
+  DBuf<AoSampleInfo> d_info;
+  std::vector<uint64_t> per_instance;
+  DBuf<float> d_ao;
+  DBuf<uint32_t> d_hits;
+  DBuf<unsigned long long> d_stats;
+  bool have_ao = false;
+
+  AoTimings timings{};
+
+  int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    err = buf;
+    return code;
+  }
+};
+
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e__ = (call);                                                                            \
+    if (e__ != cudaSuccess)                                                                              \
+      return ctx->fail(AOBAKE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+#define CKL() CK(cudaGetLastError())
+
+namespace {
+
+struct Segment {
+  uint32_t root = 0;
+  uint32_t node_count = 0;
+  float box[6] = {0, 0, 0, 0, 0, 0};
+};
+
+// Builds one 8-wide BVH over n primitive boxes into d_nodes[node_offset...]; d_leaf_prims[n]
+// receives the leaf order (relative primitive ids).
+int build_segment(AoBake* ctx, const F4* d_plo, const F4* d_phi, uint32_t n, uint32_t max_leaf, uint32_t node_offset,
+                  uint32_t prim_offset, Node8* d_nodes, uint32_t* d_leaf_prims, Segment* out) {
+  cudaStream_t st = ctx->stream;
+  out->root = node_offset;
+  if (n == 0) {
+    k_empty_node<<<1, 1, 0, st>>>(d_nodes + node_offset);
+    CKL();
+    out->node_count = 1;
+    return AOBAKE_OK;
+  }
+  DBuf<int> d_b;  // 6 centroid + 6 box bounds
+  DBuf<float> d_box;
+  DBuf<uint64_t> keys, keys_s;
+  DBuf<uint32_t> vals, vals_s, left, right, first, last, pint, pleaf, flags, wide2bin, counters;
+  DBuf<F4> ilo, ihi;
+  const uint32_t ni = n > 1 ? n - 1 : 1;
+  CK(d_b.alloc(12)); CK(d_box.alloc(6));
+  CK(keys.alloc(n)); CK(keys_s.alloc(n)); CK(vals.alloc(n)); CK(vals_s.alloc(n));
+  CK(left.alloc(ni)); CK(right.alloc(ni)); CK(first.alloc(ni)); CK(last.alloc(ni)); CK(pint.alloc(ni)); CK(pleaf.alloc(n));
+  CK(flags.alloc(ni)); CK(wide2bin.alloc(n)); CK(counters.alloc(2)); CK(ilo.alloc(ni)); CK(ihi.alloc(ni));
+  k_init_bounds<<<1, 32, 0, st>>>(d_b.p);
+  k_init_bounds<<<1, 32, 0, st>>>(d_b.p + 6);
+  k_bounds<<<std::min<unsigned>(grid_for(n, 256), 148u * 8u), 256, 0, st>>>(d_plo, d_phi, n, d_b.p, d_b.p + 6);
+  k_decode_bounds<<<1, 32, 0, st>>>(d_b.p + 6, d_box.p);
+  k_morton<<<grid_for(n, 256), 256, 0, st>>>(d_plo, d_phi, n, d_b.p, keys.p, vals.p);
+  CKL();
+  {
+    size_t tmp_bytes = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.p, keys_s.p, vals.p, vals_s.p, (int)n, 0, 63, st));
+    DBuf<uint8_t> tmp;
+    CK(tmp.alloc(tmp_bytes));
+    CK(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys.p, keys_s.p, vals.p, vals_s.p, (int)n, 0, 63, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  Lbvh L;
+  L.keys = keys_s.p; L.prim = vals_s.p; L.plo = d_plo; L.phi = d_phi;
+  L.left = left.p; L.right = right.p; L.first = first.p; L.last = last.p;
+  L.parent_int = pint.p; L.parent_leaf = pleaf.p; L.ilo = ilo.p; L.ihi = ihi.p; L.flags = flags.p; L.n = n;
+  if (n >= 2) {
+    CK(cudaMemsetAsync(flags.p, 0, ni * sizeof(uint32_t), st));
+    k_hierarchy<<<grid_for(n - 1, 256), 256, 0, st>>>(L);
+    k_refit<<<grid_for(n, 256), 256, 0, st>>>(L);
+    CKL();
+  }
+  // level-synchronous collapse into 8-wide nodes
+  CollapseArgs A;
+  A.L = L; A.nodes = d_nodes; A.wide2bin = wide2bin.p; A.leaf_prims = d_leaf_prims;
+  A.node_count = counters.p; A.prim_count = counters.p + 1; A.node_offset = node_offset; A.prim_offset = prim_offset;
+  A.max_leaf = max_leaf;
+  k_set_u32<<<1, 1, 0, st>>>(counters.p, 1u);
+  k_set_u32<<<1, 1, 0, st>>>(counters.p + 1, 0u);
+  k_set_u32<<<1, 1, 0, st>>>(wide2bin.p, n == 1 ? (0u | kLeafBit) : 0u);
+  uint32_t lb = 0, le = 1;
+  uint32_t hc[2] = {1, 0};
+  int levels = 0;
+  while (lb < le) {
+    k_collapse<<<grid_for(le - lb, 128), 128, 0, st>>>(A, lb, le);
+    CKL();
+    CK(cudaMemcpyAsync(hc, counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    lb = le;
+    le = hc[0];
+    if (++levels > 4096) return ctx->fail(AOBAKE_ERR_CUDA, "BVH collapse did not terminate");
+  }
+  if (hc[1] != n) return ctx->fail(AOBAKE_ERR_CUDA, "BVH collapse emitted %u of %u primitives", hc[1], n);
+  out->node_count = hc[0];
+  CK(cudaMemcpyAsync(out->box, d_box.p, sizeof(out->box), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return AOBAKE_OK;
+}
+
+int upload_mesh(AoBake* ctx, const AoMesh& m, DeviceMesh& dm, bool want_normals) {
+  dm.nV = m.num_vertices;
+  dm.nT = m.num_triangles;
+  if (m.num_vertices > 0xfffffff0ull || m.num_triangles > 0x7ffffff0ull)
+    return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "mesh too large for 32-bit indices");
+  if ((m.num_vertices && !m.vertices) || (m.num_triangles && !m.tri_vertex_indices))
+    return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "mesh has null vertex or index pointer");
+  const uint32_t vs = m.vertex_stride_bytes ? m.vertex_stride_bytes : 12u;
+  const uint32_t ns = m.normal_stride_bytes ? m.normal_stride_bytes : 12u;
+  CK(dm.verts.alloc(3 * dm.nV));
+  CK(dm.tris.alloc(3 * dm.nT));
+  auto copy_strided = [&](const float* src, uint32_t stride, float* dst) -> cudaError_t {
+    if (dm.nV == 0) return cudaSuccess;
+    if (stride == 12) return cudaMemcpyAsync(dst, src, 12 * dm.nV, cudaMemcpyHostToDevice, ctx->stream);
+    return cudaMemcpy2DAsync(dst, 12, src, stride, 12, dm.nV, cudaMemcpyHostToDevice, ctx->stream);
+  };
+  CK(copy_strided(m.vertices, vs, dm.verts.p));
+  if (want_normals && m.normals) {
+    CK(dm.normals.alloc(3 * dm.nV));
+    CK(copy_strided(m.normals, ns, dm.normals.p));
+  }
+  if (dm.nT) CK(cudaMemcpyAsync(dm.tris.p, m.tri_vertex_indices, 12 * dm.nT, cudaMemcpyHostToDevice, ctx->stream));
+  return AOBAKE_OK;
+}
+
+int check_scene(AoBake* ctx, const AoScene* s, const char* what) {
+  if (!s) return AOBAKE_OK;
+  if ((s->num_meshes && !s->meshes) || (s->num_instances && !s->instances))
+    return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "%s: null meshes/instances pointer", what);
+  for (uint64_t i = 0; i < s->num_instances; i++)
+    if (s->instances[i].mesh_index >= s->num_meshes)
+      return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "%s: instance %llu references mesh %u of %llu", what,
+                       (unsigned long long)i, s->instances[i].mesh_index, (unsigned long long)s->num_meshes);
+  return AOBAKE_OK;
+}
+
+int ensure_areas(AoBake* ctx) {
+  if (ctx->areas_ready) return AOBAKE_OK;
+  cudaStream_t st = ctx->stream;
+  const uint32_t ni = (uint32_t)ctx->insts.size();
+  std::vector<InstDesc> h(ni);
+  uint64_t e = 0, b = 0;
+  for (uint32_t i = 0; i < ni; i++) {
+    const HostInstance& I = ctx->insts[i];
+    const DeviceMesh& m = ctx->meshes[I.mesh];
+    memcpy(h[i].xf, I.xf, sizeof(I.xf));
+    memcpy(h[i].inv, I.inv, sizeof(I.inv));
+    h[i].verts = m.verts.p; h[i].normals = m.normals.p; h[i].tris = m.tris.p;
+    h[i].tri_begin = e; h[i].num_tris = m.nT; h[i].block_begin = b;
+    h[i].sample_begin = 0; h[i].num_samples = 0; h[i].seed = i; h[i].pad = 0;
+    e += m.nT;
+    b += (m.nT + 1023) / 1024;
+  }
+  ctx->total_tris = e;
+  ctx->total_blocks = b;
+  CK(ctx->d_inst.alloc(std::max<uint32_t>(ni, 1)));
+  CK(ctx->d_tri_area.alloc(std::max<uint64_t>(e, 1)));
+  CK(ctx->d_bsum.alloc(std::max<uint64_t>(b, 1)));
+  CK(ctx->d_inst_area.alloc(std::max<uint32_t>(ni, 1)));
+  ctx->inst_area.assign(ni, 0.0);
+  if (ni) {
+    CK(cudaMemcpyAsync(ctx->d_inst.p, h.data(), ni * sizeof(InstDesc), cudaMemcpyHostToDevice, st));
+    if (e) k_tri_areas<<<grid_for(e, 256), 256, 0, st>>>(ctx->d_inst.p, ni, e, ctx->d_tri_area.p);
+    if (b) k_block_sums<<<grid_for(b, 128), 128, 0, st>>>(ctx->d_inst.p, ni, b, ctx->d_tri_area.p, ctx->d_bsum.p);
+    k_inst_totals<<<grid_for(ni, 128), 128, 0, st>>>(ctx->d_inst.p, ni, ctx->d_bsum.p, ctx->d_inst_area.p);
+    CKL();
+    CK(cudaMemcpyAsync(ctx->inst_area.data(), ctx->d_inst_area.p, ni * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  ctx->areas_ready = true;
+  return AOBAKE_OK;
+}
+
+int alloc_samples(AoBake* ctx, uint64_t n) {
+  ctx->num_samples = n;
+  ctx->have_ao = false;
+  const uint64_t m = std::max<uint64_t>(n, 1);
+  CK(ctx->d_pos.alloc(3 * m)); CK(ctx->d_nrm.alloc(3 * m)); CK(ctx->d_fnrm.alloc(3 * m)); CK(ctx->d_info.alloc(m));
+  CK(ctx->d_ao.alloc(m)); CK(ctx->d_hits.alloc(m));
+  CK(cudaMemsetAsync(ctx->d_ao.p, 0, m * sizeof(float), ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_hits.p, 0, m * sizeof(uint32_t), ctx->stream));
+  return AOBAKE_OK;
+}
+
+BvhView bvh_view(const AoBake* ctx) {
+  BvhView v;
+  v.nodes = reinterpret_cast<const U4*>(ctx->d_nodes.p);
+  v.tris = ctx->d_tris.p;
+  v.insts = ctx->d_insts.p;
+  v.root = ctx->root;
+  v.two_level = ctx->two_level ? 1u : 0u;
+  return v;
+}
+
+struct ScopedTimer {
+  AoBake* c;
+  double t0;
+  explicit ScopedTimer(AoBake* ctx) : c(ctx), t0(now_ms()) {}
+  ~ScopedTimer() { c->timings.host_total_ms = (float)(now_ms() - t0); }
+};
+
+}  // namespace
+
+// =========================================================================================
+// C-ABI
+// =========================================================================================
+extern "C" {
+
+int aobake_default_params(AoBakeParams* p) {
+  if (!p) return AOBAKE_ERR_INVALID_ARGUMENT;
+  memset(p, 0, sizeof(*p));
+  p->device = 0;
+  p->instancing_mode = AOBAKE_INSTANCING_AUTO;
+  p->cg_max_iterations = 2000;
+  p->cg_tolerance = 1e-6f;
+  p->trace_kernel = 0;
+  p->collect_stats = 0;
+  return AOBAKE_OK;
+}
+
+const char* aobake_last_error(const AoBake* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int aobake_create(const AoBakeParams* params, AoBake** out) {
+  if (!out) return AOBAKE_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  AoBakeParams p;
+  aobake_default_params(&p);
+  if (params) p = *params;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (libaobake has no CPU fallback)";
+    return AOBAKE_ERR_NO_DEVICE;
+  }
+  if (p.device < 0 || p.device >= count) {
+    g_create_error = "device ordinal out of range";
+    return AOBAKE_ERR_INVALID_ARGUMENT;
+  }
+  if ((e = cudaSetDevice(p.device)) != cudaSuccess) {
+    g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+    return AOBAKE_ERR_CUDA;
+  }
+  AoBake* ctx = new AoBake();
+  ctx->params = p;
+  ctx->device = p.device;
+  cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, p.device);
+  if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+      ctx->d_stats.alloc(4) != cudaSuccess) {
+    g_create_error = std::string("context setup: ") + cudaGetErrorString(cudaGetLastError());
+    delete ctx;
+    return AOBAKE_ERR_CUDA;
+  }
+  ctx->stream = ctx->own_stream;
+  *out = ctx;
+  return AOBAKE_OK;
+}
+
+void aobake_destroy(AoBake* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+int aobake_set_stream(AoBake* ctx, void* s) {
+  if (!ctx) return AOBAKE_ERR_INVALID_ARGUMENT;
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->stream = s ? reinterpret_cast<cudaStream_t>(s) : ctx->own_stream;
+  return AOBAKE_OK;
+}
+int aobake_synchronize(AoBake* ctx) {
+  if (!ctx) return AOBAKE_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return AOBAKE_OK;
+}
+
+int aobake_set_scene(AoBake* ctx, const AoScene* scene, const AoScene* blockers) {
+  if (!ctx || !scene) return AOBAKE_ERR_INVALID_ARGUMENT;
+  ScopedTimer tm(ctx);
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  if (blockers && blockers->num_instances == 0) blockers = nullptr;
+  int rc;
+  if ((rc = check_scene(ctx, scene, "scene")) || (rc = check_scene(ctx, blockers, "blockers"))) return rc;
+  ctx->have_scene = false;
+  ctx->areas_ready = false;
+  ctx->num_samples = 0;
+  ctx->have_ao = false;
+  ctx->per_instance.clear();
+  ctx->meshes.clear();
+  ctx->insts.clear();
+  ctx->inst_num_verts.clear();
+
+  // ---- upload ----
+  CK(cudaEventRecord(ctx->ev0, st));
+  ctx->meshes.resize(scene->num_meshes);
+  for (uint64_t m = 0; m < scene->num_meshes; m++)
+    if ((rc = upload_mesh(ctx, scene->meshes[m], ctx->meshes[m], true))) return rc;
+  std::vector<DeviceMesh> bmeshes(blockers ? blockers->num_meshes : 0);
+  for (size_t m = 0; m < bmeshes.size(); m++)
+    if ((rc = upload_mesh(ctx, blockers->meshes[m], bmeshes[m], false))) return rc;
+  std::vector<HostInstance> binsts;
+  auto add_insts = [&](const AoScene* s, std::vector<HostInstance>& dst) {
+    for (uint64_t i = 0; i < s->num_instances; i++) {
+      HostInstance h;
+      memcpy(h.xf, s->instances[i].xform, sizeof(h.xf));
+      affine_inverse(h.xf, h.inv);
+      h.mesh = s->instances[i].mesh_index;
+      h.storage_id = s->instances[i].storage_identifier;
+      dst.push_back(h);
+    }
+  };
+  add_insts(scene, ctx->insts);
+  if (blockers) add_insts(blockers, binsts);
+  for (const HostInstance& I : ctx->insts) ctx->inst_num_verts.push_back(ctx->meshes[I.mesh].nV);
+  CK(cudaEventRecord(ctx->ev1, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaEventElapsedTime(&ctx->timings.upload_ms, ctx->ev0, ctx->ev1));
+
+  // ---- instancing mode (decision #12) ----
+  bool two_level = ctx->params.instancing_mode == AOBAKE_INSTANCING_TWO_LEVEL;
+  if (ctx->params.instancing_mode == AOBAKE_INSTANCING_AUTO) {
+    std::vector<uint32_t> refs(ctx->meshes.size(), 0), brefs(bmeshes.size(), 0);
+    for (const HostInstance& I : ctx->insts) if (++refs[I.mesh] > 1) two_level = true;
+    for (const HostInstance& I : binsts) if (++brefs[I.mesh] > 1) two_level = true;
+  }
+  ctx->two_level = two_level;
+
+  // ---- BVH build ----
+  CK(cudaEventRecord(ctx->ev0, st));
+  struct Ref { const DeviceMesh* mesh; const HostInstance* inst; };
+  std::vector<Ref> all;
+  for (const HostInstance& I : ctx->insts) all.push_back({&ctx->meshes[I.mesh], &I});
+  for (const HostInstance& I : binsts) all.push_back({&bmeshes[I.mesh], &I});
+  memset(&ctx->stats, 0, sizeof(ctx->stats));
+  ctx->stats.two_level = two_level ? 1 : 0;
+  if (!two_level) {
+    uint64_t n64 = 0;
+    for (const Ref& r : all) n64 += r.mesh->nT;
+    if (n64 > 0x7ffffff0ull) return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "flattened scene has too many triangles (%llu)", (unsigned long long)n64);
+    const uint32_t n = (uint32_t)n64;
+    DBuf<F4> soup, plo, phi;
+    DBuf<uint32_t> leaf_prims;
+    DBuf<Node8> nodes;
+    CK(soup.alloc(3ull * std::max(n, 1u))); CK(plo.alloc(std::max(n, 1u))); CK(phi.alloc(std::max(n, 1u)));
+    CK(leaf_prims.alloc(std::max(n, 1u))); CK(nodes.alloc(std::max(n, 1u)));
+    uint32_t off = 0;
+    for (const Ref& r : all) {
+      if (!r.mesh->nT) continue;
+      Xf12 xf;
+      memcpy(xf.m, r.inst->xf, sizeof(xf.m));
+      k_make_tris<<<grid_for(r.mesh->nT, 256), 256, 0, st>>>(r.mesh->verts.p, r.mesh->tris.p, (uint32_t)r.mesh->nT, xf, 0, off,
+                                                            soup.p, plo.p, phi.p);
+      off += (uint32_t)r.mesh->nT;
+    }
+    CKL();
+    Segment seg;
+    if ((rc = build_segment(ctx, plo.p, phi.p, n, 3, 0, 0, nodes.p, leaf_prims.p, &seg))) return rc;
+    CK(ctx->d_tris.alloc(3ull * std::max(n, 1u)));
+    if (n) k_gather_tris<<<grid_for(n, 256), 256, 0, st>>>(soup.p, leaf_prims.p, n, 0, ctx->d_tris.p);
+    CKL();
+    CK(ctx->d_nodes.alloc(seg.node_count));
+    CK(cudaMemcpyAsync(ctx->d_nodes.p, nodes.p, seg.node_count * sizeof(Node8), cudaMemcpyDeviceToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    ctx->d_insts.release();
+    ctx->root = 0;
+    ctx->stats.num_bvh_nodes = seg.node_count;
+    ctx->stats.num_bvh_triangles = n;
+  } else {
+    // one BLAS per mesh (scene meshes, then blocker meshes), object space
+    std::vector<const DeviceMesh*> ml;
+    for (const DeviceMesh& m : ctx->meshes) ml.push_back(&m);
+    for (const DeviceMesh& m : bmeshes) ml.push_back(&m);
+    uint64_t tri_total = 0, node_cap = 0;
+    for (const DeviceMesh* m : ml) { tri_total += m->nT; node_cap += std::max<uint64_t>(m->nT, 1); }
+    node_cap += std::max<uint64_t>(all.size(), 1);
+    if (tri_total > 0x7ffffff0ull || node_cap > 0x7ffffff0ull) return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "scene too large");
+    DBuf<Node8> nodes;
+    CK(nodes.alloc(node_cap));
+    CK(ctx->d_tris.alloc(3ull * std::max<uint64_t>(tri_total, 1)));
+    std::vector<Segment> segs(ml.size());
+    uint32_t node_off = 0, prim_off = 0;
+    for (size_t mi = 0; mi < ml.size(); mi++) {
+      const DeviceMesh* m = ml[mi];
+      const uint32_t n = (uint32_t)m->nT;
+      DBuf<F4> soup, plo, phi;
+      DBuf<uint32_t> leaf_prims;
+      CK(soup.alloc(3ull * std::max(n, 1u))); CK(plo.alloc(std::max(n, 1u))); CK(phi.alloc(std::max(n, 1u))); CK(leaf_prims.alloc(std::max(n, 1u)));
+      Xf12 idn;
+      memset(&idn, 0, sizeof(idn));
+      if (n) k_make_tris<<<grid_for(n, 256), 256, 0, st>>>(m->verts.p, m->tris.p, n, idn, 1, 0, soup.p, plo.p, phi.p);
+      CKL();
+      if ((rc = build_segment(ctx, plo.p, phi.p, n, 3, node_off, prim_off, nodes.p, leaf_prims.p, &segs[mi]))) return rc;
+      if (n) k_gather_tris<<<grid_for(n, 256), 256, 0, st>>>(soup.p, leaf_prims.p, n, 0, ctx->d_tris.p + 3ull * prim_off);
+      CKL();
+      CK(cudaStreamSynchronize(st));
+      node_off += segs[mi].node_count;
+      prim_off += n;
+    }
+    // TLAS over instance world boxes (8 transformed corners of the BLAS box, padded)
+    const uint32_t nI = (uint32_t)all.size();
+    std::vector<F4> hlo(std::max(nI, 1u)), hhi(std::max(nI, 1u));
+    std::vector<uint32_t> inst_blas(nI);
+    for (uint32_t i = 0; i < nI; i++) {
+      const bool is_blocker = i >= ctx->insts.size();
+      const uint32_t mi = all[i].inst->mesh + (is_blocker ? (uint32_t)ctx->meshes.size() : 0u);
+      inst_blas[i] = mi;
+      const float* b = segs[mi].box;
+      F4 lo, hi;
+      lo.x = lo.y = lo.z = 3.0e38f; hi.x = hi.y = hi.z = -3.0e38f; lo.w = hi.w = 0.f;
+      if (ml[mi]->nT == 0) { lo.x = lo.y = lo.z = 0.f; hi = lo; }
+      else {
+        for (int c = 0; c < 8; c++) {
+          V3 p = xf_point(all[i].inst->xf, v3((c & 1) ? b[3] : b[0], (c & 2) ? b[4] : b[1], (c & 4) ? b[5] : b[2]));
+          lo.x = fminf(lo.x, p.x); lo.y = fminf(lo.y, p.y); lo.z = fminf(lo.z, p.z);
+          hi.x = fmaxf(hi.x, p.x); hi.y = fmaxf(hi.y, p.y); hi.z = fmaxf(hi.z, p.z);
+        }
+        const float px = 3.8e-6f * fmaxf(fabsf(lo.x), fabsf(hi.x)), py = 3.8e-6f * fmaxf(fabsf(lo.y), fabsf(hi.y)),
+                    pz = 3.8e-6f * fmaxf(fabsf(lo.z), fabsf(hi.z));
+        lo.x -= px; lo.y -= py; lo.z -= pz; hi.x += px; hi.y += py; hi.z += pz;
+      }
+      hlo[i] = lo; hhi[i] = hi;
+    }
+    DBuf<F4> plo, phi;
+    DBuf<uint32_t> leaf_insts;
+    CK(plo.alloc(std::max(nI, 1u))); CK(phi.alloc(std::max(nI, 1u))); CK(leaf_insts.alloc(std::max(nI, 1u)));
+    if (nI) {
+      CK(cudaMemcpyAsync(plo.p, hlo.data(), nI * sizeof(F4), cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(phi.p, hhi.data(), nI * sizeof(F4), cudaMemcpyHostToDevice, st));
+    }
+    Segment tl;
+    if ((rc = build_segment(ctx, plo.p, phi.p, nI, 1, node_off, 0, nodes.p, leaf_insts.p, &tl))) return rc;
+    std::vector<uint32_t> order(nI);
+    if (nI) CK(cudaMemcpy(order.data(), leaf_insts.p, nI * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    std::vector<F4> recs(4ull * std::max(nI, 1u));
+    for (uint32_t k = 0; k < nI; k++) {
+      const HostInstance* I = all[order[k]].inst;
+      for (int r = 0; r < 3; r++) { F4 f; f.x = I->inv[4 * r]; f.y = I->inv[4 * r + 1]; f.z = I->inv[4 * r + 2]; f.w = I->inv[4 * r + 3]; recs[4ull * k + r] = f; }
+      F4 f;
+      uint32_t rootidx = segs[inst_blas[order[k]]].root, id = order[k];
+      memcpy(&f.x, &rootidx, 4); memcpy(&f.y, &id, 4); f.z = 0.f; f.w = 0.f;
+      recs[4ull * k + 3] = f;
+    }
+    CK(ctx->d_insts.alloc(recs.size()));
+    CK(cudaMemcpy(ctx->d_insts.p, recs.data(), recs.size() * sizeof(F4), cudaMemcpyHostToDevice));
+    const uint32_t total_nodes = node_off + tl.node_count;
+    CK(ctx->d_nodes.alloc(total_nodes));
+    CK(cudaMemcpyAsync(ctx->d_nodes.p, nodes.p, total_nodes * sizeof(Node8), cudaMemcpyDeviceToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    ctx->root = tl.root;
+    ctx->stats.num_bvh_nodes = total_nodes;
+    ctx->stats.num_bvh_triangles = tri_total;
+    ctx->stats.num_tlas_instances = nI;
+  }
+  ctx->stats.bvh_bytes = ctx->stats.num_bvh_nodes * sizeof(Node8) + ctx->stats.num_bvh_triangles * 48 + ctx->stats.num_tlas_instances * 64;
+  CK(cudaEventRecord(ctx->ev1, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaEventElapsedTime(&ctx->timings.bvh_build_ms, ctx->ev0, ctx->ev1));
+  ctx->have_scene = true;
+  return AOBAKE_OK;
+}
+
+int aobake_distribute_samples(AoBake* ctx, size_t min_per_tri, size_t requested, size_t* per_instance, size_t* total) {
+  if (!ctx || !per_instance) return AOBAKE_ERR_INVALID_ARGUMENT;
+  if (!ctx->have_scene) return ctx->fail(AOBAKE_ERR_STATE, "distribute_samples before set_scene");
+  ScopedTimer tm(ctx);
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = ensure_areas(ctx))) return rc;
+  // distribute_samples_generic over instances (bake_sample_internal.h), host side:
+  // the per-instance areas come from the device's fixed-shape sums.
+  const size_t n = ctx->insts.size();
+  std::vector<uint64_t> mins(n);
+  uint64_t summin = 0;
+  for (size_t i = 0; i < n; i++) { mins[i] = (uint64_t)min_per_tri * ctx->meshes[ctx->insts[i].mesh].nT; summin += mins[i]; }
+  const uint64_t N = std::max<uint64_t>(requested, summin);
+  double total_area = 0.0;
+  for (size_t b = 0; b < n; b += 1024) {
+    double s = 0.0;
+    for (size_t i = b; i < std::min(n, b + 1024); i++) s = s + ctx->inst_area[i];
+    total_area = total_area + s;
+  }
+  const uint64_t Na = N - summin;
+  uint64_t assigned = 0;
+  for (size_t i = 0; i < n; i++) {
+    uint64_t c = mins[i];
+    if (Na > 0 && total_area > 0.0) c += (uint64_t)(((double)Na * ctx->inst_area[i]) / total_area);
+    per_instance[i] = c;
+    assigned += c;
+  }
+  if (assigned > N) return ctx->fail(AOBAKE_ERR_SAMPLE_OVERFLOW, "instance budget floors exceed the total");
+  uint64_t left = N - assigned;
+  if (n == 0 && left) return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "samples requested for an empty scene");
+  for (size_t i = 0; left > 0; i = (i + 1) % n, left--) per_instance[i] += 1;
+  if (total) *total = N;
+  return AOBAKE_OK;
+}
+
+int aobake_sample_instances(AoBake* ctx, const size_t* per_instance, size_t min_per_tri, AoSamples* host_out) {
+  if (!ctx || !per_instance) return AOBAKE_ERR_INVALID_ARGUMENT;
+  if (!ctx->have_scene) return ctx->fail(AOBAKE_ERR_STATE, "sample_instances before set_scene");
+  ScopedTimer tm(ctx);
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  int rc;
+  if ((rc = ensure_areas(ctx))) return rc;
+  const uint32_t ni = (uint32_t)ctx->insts.size();
+  uint64_t total = 0;
+  std::vector<InstDesc> h(ni);
+  if (ni) CK(cudaMemcpy(h.data(), ctx->d_inst.p, ni * sizeof(InstDesc), cudaMemcpyDeviceToHost));
+  for (uint32_t i = 0; i < ni; i++) {
+    if (per_instance[i] < min_per_tri * h[i].num_tris)
+      return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "instance %u: %llu samples < minimum %llu", i, (unsigned long long)per_instance[i],
+                       (unsigned long long)(min_per_tri * h[i].num_tris));
+    if (per_instance[i] && !h[i].num_tris) return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "instance %u has no triangles to sample", i);
+    h[i].sample_begin = total;
+    h[i].num_samples = per_instance[i];
+    total += per_instance[i];
+  }
+  if (host_out && host_out->num_samples != total)
+    return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "host_out->num_samples %llu != sum(per_instance) %llu",
+                     (unsigned long long)host_out->num_samples, (unsigned long long)total);
+  if ((rc = alloc_samples(ctx, total))) return rc;
+  ctx->per_instance.assign(per_instance, per_instance + ni);
+  CK(cudaEventRecord(ctx->ev0, st));
+  const uint64_t E = ctx->total_tris;
+  if (total && E) {
+    CK(cudaMemcpyAsync(ctx->d_inst.p, h.data(), ni * sizeof(InstDesc), cudaMemcpyHostToDevice, st));
+    DBuf<uint64_t> counts, offs, final_off;
+    DBuf<uint32_t> final_cnt;
+    DBuf<long long> leftover;
+    DBuf<int> status;
+    CK(counts.alloc(E)); CK(offs.alloc(E)); CK(final_off.alloc(E + 1)); CK(final_cnt.alloc(E)); CK(leftover.alloc(ni)); CK(status.alloc(1));
+    CK(cudaMemsetAsync(status.p, 0, sizeof(int), st));
+    k_tri_counts<<<grid_for(E, 256), 256, 0, st>>>(ctx->d_inst.p, ni, E, ctx->d_tri_area.p, ctx->d_inst_area.p, (uint64_t)min_per_tri, counts.p);
+    CKL();
+    {
+      size_t tmp_bytes = 0;
+      CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts.p, offs.p, (long long)E, st));
+      DBuf<uint8_t> tmp;
+      CK(tmp.alloc(tmp_bytes));
+      CK(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, counts.p, offs.p, (long long)E, st));
+      CK(cudaStreamSynchronize(st));
+    }
+    k_inst_leftover<<<grid_for(ni, 128), 128, 0, st>>>(ctx->d_inst.p, ni, offs.p, counts.p, leftover.p, status.p);
+    k_final_offsets<<<grid_for(E + 1, 256), 256, 0, st>>>(ctx->d_inst.p, ni, E, offs.p, counts.p, leftover.p, final_off.p, final_cnt.p, total);
+    CKL();
+    int hs = 0;
+    CK(cudaMemcpyAsync(&hs, status.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (hs) return ctx->fail(AOBAKE_ERR_SAMPLE_OVERFLOW, "area-proportional floors exceeded an instance budget (status %d)", hs);
+    k_place_samples<<<grid_for(total, 256), 256, 0, st>>>(ctx->d_inst.p, ni, E, final_off.p, final_cnt.p, ctx->d_tri_area.p, total, ctx->d_pos.p,
+                                                         ctx->d_nrm.p, ctx->d_fnrm.p, ctx->d_info.p);
+    CKL();
+    CK(cudaStreamSynchronize(st));
+  }
+  CK(cudaEventRecord(ctx->ev1, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaEventElapsedTime(&ctx->timings.sample_ms, ctx->ev0, ctx->ev1));
+  if (host_out && total) {
+    CK(cudaMemcpyAsync(host_out->sample_positions, ctx->d_pos.p, 12 * total, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(host_out->sample_normals, ctx->d_nrm.p, 12 * total, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(host_out->sample_face_normals, ctx->d_fnrm.p, 12 * total, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(host_out->sample_infos, ctx->d_info.p, sizeof(AoSampleInfo) * total, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  return AOBAKE_OK;
+}
+
+int aobake_set_samples(AoBake* ctx, const AoSamples* s, const size_t* per_instance) {
+  if (!ctx || !s) return AOBAKE_ERR_INVALID_ARGUMENT;
+  ScopedTimer tm(ctx);
+  CK(cudaSetDevice(ctx->device));
+  const uint64_t n = s->num_samples;
+  if (n && (!s->sample_positions || !s->sample_normals || !s->sample_face_normals))
+    return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "null sample arrays");
+  int rc;
+  if ((rc = alloc_samples(ctx, n))) return rc;
+  ctx->per_instance.clear();
+  if (per_instance) {
+    uint64_t sum = 0;
+    for (size_t i = 0; i < ctx->insts.size(); i++) sum += per_instance[i];
+    if (sum != n) return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "sum(per_instance) != num_samples");
+    ctx->per_instance.assign(per_instance, per_instance + ctx->insts.size());
+  }
+  if (n) {
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->d_pos.p, s->sample_positions, 12 * n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_nrm.p, s->sample_normals, 12 * n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_fnrm.p, s->sample_face_normals, 12 * n, cudaMemcpyHostToDevice, st));
+    if (s->sample_infos) CK(cudaMemcpyAsync(ctx->d_info.p, s->sample_infos, sizeof(AoSampleInfo) * n, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  return AOBAKE_OK;
+}
+
+size_t aobake_num_samples(const AoBake* ctx) { return ctx ? ctx->num_samples : 0; }
+
+int aobake_compute_ao_range(AoBake* ctx, size_t begin, size_t end, int rays_per_sample, float offset, float maxdist, float* host_ao) {
+  if (!ctx) return AOBAKE_ERR_INVALID_ARGUMENT;
+  if (!ctx->have_scene) return ctx->fail(AOBAKE_ERR_STATE, "compute_ao before set_scene");
+  if (begin > end || end > ctx->num_samples) return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "sample range [%zu,%zu) outside [0,%llu)", begin, end, (unsigned long long)ctx->num_samples);
+  if (rays_per_sample < 1) return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "rays_per_sample must be >= 1");
+  ScopedTimer tm(ctx);
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int q = sqrt_rays(rays_per_sample);
+  if (q < 1 || q > 255) return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "sqrt(rays_per_sample) must be in [1,255]");
+  const uint64_t n = end - begin;
+  ctx->timings.rays_traced = n * (uint64_t)q * q;
+  ctx->timings.trace_ms = 0.f;
+  if (n == 0) return AOBAKE_OK;
+  const bool stats = ctx->params.collect_stats != 0;
+  SampleView S{ctx->d_pos.p, ctx->d_nrm.p, ctx->d_fnrm.p};
+  const BvhView bvh = bvh_view(ctx);
+  if (stats) CK(cudaMemsetAsync(ctx->d_stats.p, 0, 4 * sizeof(unsigned long long), st));
+  CK(cudaEventRecord(ctx->ev0, st));
+  {
+    // simple variant: enough (sample block, strata chunk) items to fill the machine
+    const uint64_t n_blocks = (n + 31) / 32;
+    const uint64_t want = (uint64_t)ctx->sm_count * 64ull * 4ull;
+    uint32_t n_chunks = 1;
+    while (n_blocks * n_chunks < want && n_chunks * 2 <= (uint32_t)(q * q)) n_chunks *= 2;
+    if (n_chunks > 1) CK(cudaMemsetAsync(ctx->d_hits.p + begin, 0, n * sizeof(uint32_t), st));
+    const uint64_t warps = n_blocks * n_chunks;
+    const unsigned grid = grid_for(warps * 32, 256);
+    if (stats)
+      k_ao_simple<true><<<grid, 256, 0, st>>>(bvh, S, begin, end, q, offset, maxdist, n_chunks, ctx->d_hits.p + begin, ctx->d_stats.p);
+    else
+      k_ao_simple<false><<<grid, 256, 0, st>>>(bvh, S, begin, end, q, offset, maxdist, n_chunks, ctx->d_hits.p + begin, ctx->d_stats.p);
+    CKL();
+  }
+  k_ao_finalize<<<grid_for(n, 256), 256, 0, st>>>(ctx->d_hits.p + begin, n, (float)(q * q), ctx->d_ao.p + begin);
+  CKL();
+  CK(cudaEventRecord(ctx->ev1, st));
+  if (host_ao) CK(cudaMemcpyAsync(host_ao, ctx->d_ao.p + begin, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaEventElapsedTime(&ctx->timings.trace_ms, ctx->ev0, ctx->ev1));
+  if (stats) {
+    unsigned long long hs[4];
+    CK(cudaMemcpy(hs, ctx->d_stats.p, sizeof(hs), cudaMemcpyDeviceToHost));
+    ctx->stats.node_visits = hs[0]; ctx->stats.triangle_tests = hs[1]; ctx->stats.instance_entries = hs[2];
+    ctx->stats.rays = ctx->timings.rays_traced;
+  }
+  ctx->have_ao = true;
+  return AOBAKE_OK;
+}
+
+int aobake_compute_ao(AoBake* ctx, int rays_per_sample, float offset, float maxdist, float* host_ao) {
+  if (!ctx) return AOBAKE_ERR_INVALID_ARGUMENT;
+  return aobake_compute_ao_range(ctx, 0, ctx->num_samples, rays_per_sample, offset, maxdist, host_ao);
+}
+
+int aobake_get_ao_device(AoBake* ctx, float** d_ao, size_t* n) {
+  if (!ctx || !d_ao) return AOBAKE_ERR_INVALID_ARGUMENT;
+  *d_ao = ctx->d_ao.p;
+  if (n) *n = ctx->num_samples;
+  return AOBAKE_OK;
+}
+int aobake_set_ao(AoBake* ctx, const float* host_ao) {
+  if (!ctx || !host_ao) return AOBAKE_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->num_samples) CK(cudaMemcpyAsync(ctx->d_ao.p, host_ao, ctx->num_samples * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->have_ao = true;
+  return AOBAKE_OK;
+}
+int aobake_get_hit_counts(AoBake* ctx, uint32_t* host_counts) {
+  if (!ctx || !host_counts) return AOBAKE_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->num_samples) CK(cudaMemcpyAsync(host_counts, ctx->d_hits.p, ctx->num_samples * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return AOBAKE_OK;
+}
+
+int aobake_map_ao_to_vertices(AoBake* ctx, int mode, float weight, float* const* host_vertex_ao) {
+  if (!ctx || !host_vertex_ao) return AOBAKE_ERR_INVALID_ARGUMENT;
+  if (!ctx->have_scene || !ctx->have_ao) return ctx->fail(AOBAKE_ERR_STATE, "map_ao_to_vertices needs a scene and AO values");
+  if (ctx->per_instance.size() != ctx->insts.size()) return ctx->fail(AOBAKE_ERR_STATE, "per-instance sample counts unknown (pass them to set_samples)");
+  if (mode != AOBAKE_FILTER_AREA_BASED && mode != AOBAKE_FILTER_LEAST_SQUARES) return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "invalid filter mode %d", mode);
+  ScopedTimer tm(ctx);
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  CK(cudaEventRecord(ctx->ev0, st));
+  ctx->timings.cg_iterations = 0;
+  uint64_t base = 0;
+  for (size_t ii = 0; ii < ctx->insts.size(); ii++) {
+    const HostInstance& I = ctx->insts[ii];
+    const DeviceMesh& m = ctx->meshes[I.mesh];
+    const uint64_t nV = m.nV, nT = m.nT, cnt = ctx->per_instance[ii];
+    DBuf<float> d_out;
+    CK(d_out.alloc(std::max<uint64_t>(nV, 1)));
+    if (mode == AOBAKE_FILTER_AREA_BASED) {
+      DBuf<double> num, wgt;
+      CK(num.alloc(std::max<uint64_t>(nV, 1))); CK(wgt.alloc(std::max<uint64_t>(nV, 1)));
+      CK(cudaMemsetAsync(num.p, 0, num.n * sizeof(double), st));
+      CK(cudaMemsetAsync(wgt.p, 0, wgt.n * sizeof(double), st));
+      if (cnt) k_area_scatter<<<grid_for(cnt, 256), 256, 0, st>>>(ctx->d_info.p, ctx->d_ao.p, base, cnt, m.tris.p, num.p, wgt.p);
+      if (nV) k_area_final<<<grid_for(nV, 256), 256, 0, st>>>(num.p, wgt.p, nV, d_out.p);
+      CKL();
+      CK(cudaStreamSynchronize(st));
+    } else {
+      // matrix-free Jacobi-PCG on (M + w R) x = b, fp64
+      const double w = weight;
+      DBuf<double> Mt, rhs, diag, x, r, z, p, Ap, scal;
+      DBuf<uint8_t> fixed;
+      DBuf<LsEdge> edges;
+      DBuf<uint32_t> ecount;
+      const uint64_t v1 = std::max<uint64_t>(nV, 1);
+      CK(Mt.alloc(6 * std::max<uint64_t>(nT, 1))); CK(rhs.alloc(v1)); CK(diag.alloc(v1)); CK(x.alloc(v1)); CK(r.alloc(v1)); CK(z.alloc(v1));
+      CK(p.alloc(v1)); CK(Ap.alloc(v1)); CK(scal.alloc(8)); CK(fixed.alloc(v1)); CK(ecount.alloc(1));
+      CK(cudaMemsetAsync(Mt.p, 0, Mt.n * sizeof(double), st));
+      CK(cudaMemsetAsync(rhs.p, 0, v1 * sizeof(double), st));
+      CK(cudaMemsetAsync(diag.p, 0, v1 * sizeof(double), st));
+      CK(cudaMemsetAsync(ecount.p, 0, sizeof(uint32_t), st));
+      if (cnt) k_ls_mass<<<grid_for(cnt, 256), 256, 0, st>>>(ctx->d_info.p, ctx->d_ao.p, base, cnt, m.tris.p, Mt.p, rhs.p);
+      CKL();
+      uint32_t nE = 0;
+      if (weight != 0.0f && nT) {
+        const uint64_t nH = 3 * nT;
+        DBuf<uint64_t> keys, keys_s;
+        DBuf<uint32_t> vals, vals_s;
+        CK(keys.alloc(nH)); CK(keys_s.alloc(nH)); CK(vals.alloc(nH)); CK(vals_s.alloc(nH));
+        k_ls_halfedges<<<grid_for(nH, 256), 256, 0, st>>>(m.tris.p, nT, keys.p, vals.p);
+        CKL();
+        size_t tmp_bytes = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.p, keys_s.p, vals.p, vals_s.p, (long long)nH, 0, 64, st));
+        DBuf<uint8_t> tmp;
+        CK(tmp.alloc(tmp_bytes));
+        CK(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys.p, keys_s.p, vals.p, vals_s.p, (long long)nH, 0, 64, st));
+        CK(edges.alloc(nH / 2 + 1));
+        Xf12 xf;
+        memcpy(xf.m, I.xf, sizeof(xf.m));
+        k_ls_edges<<<grid_for(nH, 256), 256, 0, st>>>(keys_s.p, vals_s.p, nH, m.tris.p, m.verts.p, xf, edges.p, ecount.p);
+        CKL();
+        CK(cudaMemcpyAsync(&nE, ecount.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+      }
+      const uint64_t nwork = std::max<uint64_t>(nT, nE);
+      if (nwork) k_ls_diag<<<grid_for(nwork, 256), 256, 0, st>>>(m.tris.p, nT, Mt.p, edges.p, nE, w, diag.p);
+      if (nV) {
+        k_ls_fix<<<grid_for(nV, 256), 256, 0, st>>>(diag.p, rhs.p, fixed.p, nV);
+        k_ls_init<<<grid_for(nV, 256), 256, 0, st>>>(rhs.p, diag.p, r.p, z.p, p.p, x.p, nV);
+      }
+      CKL();
+      // scal: [0]=|b|^2 [1]=rz_old [2]=pAp [3]=rz_new [4]=|r|^2
+      const unsigned dot_grid = std::min<unsigned>(grid_for(v1, 256), (unsigned)ctx->sm_count * 8u);
+      CK(cudaMemsetAsync(scal.p, 0, 8 * sizeof(double), st));
+      if (nV) {
+        k_dot<<<dot_grid, 256, 0, st>>>(rhs.p, rhs.p, nV, scal.p + 0);
+        k_dot<<<dot_grid, 256, 0, st>>>(r.p, z.p, nV, scal.p + 1);
+      }
+      double hs[8];
+      CK(cudaMemcpyAsync(hs, scal.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      const double bnorm2 = hs[0];
+      int it = 0;
+      if (nV && bnorm2 > 0.0) {
+        const double tol2 = (double)ctx->params.cg_tolerance * (double)ctx->params.cg_tolerance * bnorm2;
+        double rr = bnorm2;
+        for (; it < ctx->params.cg_max_iterations && rr > tol2; it++) {
+          CK(cudaMemsetAsync(Ap.p, 0, nV * sizeof(double), st));
+          CK(cudaMemsetAsync(scal.p + 2, 0, 3 * sizeof(double), st));
+          if (nwork) k_ls_apply<<<grid_for(nwork, 256), 256, 0, st>>>(m.tris.p, nT, Mt.p, edges.p, nE, w, p.p, Ap.p);
+          k_ls_fix_apply<<<grid_for(nV, 256), 256, 0, st>>>(fixed.p, p.p, Ap.p, nV);
+          k_dot<<<dot_grid, 256, 0, st>>>(p.p, Ap.p, nV, scal.p + 2);
+          k_ls_update<<<grid_for(nV, 256), 256, 0, st>>>(scal.p, 1, 2, p.p, Ap.p, diag.p, x.p, r.p, z.p, nV);
+          k_dot<<<dot_grid, 256, 0, st>>>(r.p, z.p, nV, scal.p + 3);
+          k_dot<<<dot_grid, 256, 0, st>>>(r.p, r.p, nV, scal.p + 4);
+          k_ls_dir<<<grid_for(nV, 256), 256, 0, st>>>(scal.p, 3, 1, z.p, p.p, nV);
+          CKL();
+          CK(cudaMemcpyAsync(hs, scal.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
+          CK(cudaStreamSynchronize(st));
+          if (!(hs[2] > 0.0)) return ctx->fail(AOBAKE_ERR_SOLVER, "CG breakdown: p.Ap = %g at iteration %d", hs[2], it);
+          rr = hs[4];
+          CK(cudaMemcpyAsync(scal.p + 1, scal.p + 3, sizeof(double), cudaMemcpyDeviceToDevice, st));
+        }
+        if (rr > tol2) return ctx->fail(AOBAKE_ERR_SOLVER, "CG did not reach %g in %d iterations (|r|/|b| = %g)", (double)ctx->params.cg_tolerance, it, sqrt(rr / bnorm2));
+      } else if (nV) {
+        CK(cudaMemsetAsync(x.p, 0, nV * sizeof(double), st));
+      }
+      ctx->timings.cg_iterations += it;
+      if (nV) k_d2f<<<grid_for(nV, 256), 256, 0, st>>>(x.p, d_out.p, nV);
+      CKL();
+      CK(cudaStreamSynchronize(st));
+    }
+    if (nV && host_vertex_ao[ii]) CK(cudaMemcpyAsync(host_vertex_ao[ii], d_out.p, nV * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    base += cnt;
+  }
+  CK(cudaEventRecord(ctx->ev1, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaEventElapsedTime(&ctx->timings.filter_ms, ctx->ev0, ctx->ev1));
+  return AOBAKE_OK;
+}
+
+int aobake_make_ground_plane(const float bbox_min[3], const float bbox_max[3], int upaxis, float scale_factor, float offset_factor,
+                             float* verts, uint32_t* tris) {
+  if (!bbox_min || !bbox_max || !verts || !tris || upaxis < 0 || upaxis > 5) return AOBAKE_ERR_INVALID_ARGUMENT;
+  const int axis = upaxis % 3, a1 = (axis + 1) % 3, a2 = (axis + 2) % 3;
+  const bool flip = upaxis >= 3;
+  float ext = 0.0f;
+  for (int k = 0; k < 3; k++) ext = std::max(ext, bbox_max[k] - bbox_min[k]);
+  const float h = flip ? bbox_max[axis] + offset_factor * ext : bbox_min[axis] - offset_factor * ext;
+  const float c1 = 0.5f * (bbox_min[a1] + bbox_max[a1]), c2 = 0.5f * (bbox_min[a2] + bbox_max[a2]);
+  const float h1 = 0.5f * scale_factor * (bbox_max[a1] - bbox_min[a1]), h2 = 0.5f * scale_factor * (bbox_max[a2] - bbox_min[a2]);
+  const float s1[4] = {-1, 1, 1, -1}, s2[4] = {-1, -1, 1, 1};
+  for (int i = 0; i < 4; i++) {
+    verts[3 * i + axis] = h;
+    verts[3 * i + a1] = c1 + s1[i] * h1;
+    verts[3 * i + a2] = c2 + s2[i] * h2;
+  }
+  const uint32_t up[6] = {0, 1, 2, 0, 2, 3}, dn[6] = {0, 2, 1, 0, 3, 2};
+  for (int i = 0; i < 6; i++) tris[i] = flip ? dn[i] : up[i];
+  return AOBAKE_OK;
+}
+
+int aobake_trace_rays(AoBake* ctx, const float* rays, size_t n, uint8_t* hit) {
+  if (!ctx || (n && (!rays || !hit))) return AOBAKE_ERR_INVALID_ARGUMENT;
+  if (!ctx->have_scene) return ctx->fail(AOBAKE_ERR_STATE, "trace_rays before set_scene");
+  ScopedTimer tm(ctx);
+  CK(cudaSetDevice(ctx->device));
+  if (!n) return AOBAKE_OK;
+  cudaStream_t st = ctx->stream;
+  DBuf<float> d_rays;
+  DBuf<uint8_t> d_hit;
+  CK(d_rays.alloc(8 * n)); CK(d_hit.alloc(n));
+  CK(cudaMemcpyAsync(d_rays.p, rays, 32 * n, cudaMemcpyHostToDevice, st));
+  k_trace_rays<<<grid_for(n, 128), 128, 0, st>>>(bvh_view(ctx), d_rays.p, n, d_hit.p);
+  CKL();
+  CK(cudaMemcpyAsync(hit, d_hit.p, n, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return AOBAKE_OK;
+}
+
+int aobake_dump_rays(AoBake* ctx, size_t begin, size_t end, int rays_per_sample, float offset, float maxdist, float* out) {
+  if (!ctx || !out) return AOBAKE_ERR_INVALID_ARGUMENT;
+  if (begin > end || end > ctx->num_samples) return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "sample range outside the resident samples");
+  ScopedTimer tm(ctx);
+  CK(cudaSetDevice(ctx->device));
+  const int q = sqrt_rays(rays_per_sample);
+  const uint64_t n = (uint64_t)(end - begin) * q * q;
+  if (!n) return AOBAKE_OK;
+  cudaStream_t st = ctx->stream;
+  DBuf<float> d_rays;
+  CK(d_rays.alloc(8 * n));
+  SampleView S{ctx->d_pos.p, ctx->d_nrm.p, ctx->d_fnrm.p};
+  k_dump_rays<<<grid_for(n, 256), 256, 0, st>>>(S, begin, end, q, offset, maxdist, d_rays.p);
+  CKL();
+  CK(cudaMemcpyAsync(out, d_rays.p, 32 * n, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return AOBAKE_OK;
+}
+
+int aobake_get_timings(AoBake* ctx, AoTimings* out) {
+  if (!ctx || !out) return AOBAKE_ERR_INVALID_ARGUMENT;
+  *out = ctx->timings;
+  return AOBAKE_OK;
+}
+int aobake_get_stats(AoBake* ctx, AoStats* out) {
+  if (!ctx || !out) return AOBAKE_ERR_INVALID_ARGUMENT;
+  *out = ctx->stats;
+  return AOBAKE_OK;
+}
+
+}  // extern "C"

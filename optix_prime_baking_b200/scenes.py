@@ -190,7 +190,7 @@ def ground_plane(bbox_min, bbox_max, upaxis: int = 1, scale_factor: float = 100.
         v[i, axis] = h
         v[i, a1] = c1 + np.float32(s1) * h1
         v[i, a2] = c2 + np.float32(s2) * h2
-    t = np.array([[0, 1, 2], [0, 2, 3]] if flip else [[0, 2, 1], [0, 3, 2]], dtype=np.uint32)
+    t = np.array([[0, 2, 1], [0, 3, 2]] if flip else [[0, 1, 2], [0, 2, 3]], dtype=np.uint32)
     return Mesh(v, t, None)
 
 

@@ -765,7 +765,7 @@ void ao_oracle_make_ground_plane(const float* bbox_min, const float* bbox_max, i
     verts[3 * i + a1] = c1 + s1[i] * h1;
     verts[3 * i + a2] = c2 + s2[i] * h2;
   }
-  const uint32_t up[6] = {0, 2, 1, 0, 3, 2}, dn[6] = {0, 1, 2, 0, 2, 3};
+  const uint32_t up[6] = {0, 1, 2, 0, 2, 3}, dn[6] = {0, 2, 1, 0, 3, 2};
   for (int i = 0; i < 6; i++) tris[i] = flip ? dn[i] : up[i];
 }
 

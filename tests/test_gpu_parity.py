@@ -1,0 +1,254 @@
+"""GPU parity tests: the CUDA path (through the C-ABI, ctypes) against the CPU oracle on the
+same seeded inputs.  Tolerances are BASELINE.json's: bit-exact sample indices, >= 99.99 %
+per-ray hit/miss agreement on identical ray sets with disagreements only next to an edge or
+a t bound, per-vertex AO within 1e-3."""
+import numpy as np
+import pytest
+
+from optix_prime_baking_b200 import scenes
+from optix_prime_baking_b200.scenes import Instance, Mesh, Scene
+
+from .oracle_binding import Oracle
+
+pytestmark = pytest.mark.gpu
+
+HIT_AGREEMENT = 0.9999      # north_star: >= 99.99 % per-ray agreement
+EDGE_MARGIN = 1e-6 * 50     # disagreements must sit within ~1e-6 (relative) of an edge / t bound;
+                            # margin is measured in barycentric units of the sheared triangle, allow slack
+VERTEX_AO_TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def api():
+    from optix_prime_baking_b200 import api as _api
+    _api.load_library()
+    return _api
+
+
+def small_scenes():
+    out = {}
+    out["sphere_ground"] = scenes.config1_sphere(48, 48)
+    out["heightfield"] = scenes.config2_heightfield(96, seed=1)
+    sc, _ = scenes.config3_bigmesh(80, seed=3)
+    out["warped_ground"] = (sc, scenes.ground_blockers(sc))
+    out["instanced"] = scenes.config4_instanced(grid=2, stacks=20, slices=20, with_ground=True)
+    return out
+
+
+SCENES = small_scenes()
+
+
+def assert_samples_equal(a, b):
+    assert a.n == b.n
+    assert np.array_equal(a.infos["tri_idx"], b.infos["tri_idx"]), "tri_idx must be bit-exact"
+    for name in ("bary", "dA"):
+        assert np.array_equal(a.infos[name].view(np.uint32), b.infos[name].view(np.uint32)), name
+    for x, y, name in ((a.positions, b.positions, "positions"), (a.normals, b.normals, "normals"),
+                       (a.face_normals, b.face_normals, "face_normals")):
+        assert np.array_equal(x.view(np.uint32), y.view(np.uint32)), name
+
+
+@pytest.mark.parametrize("name", list(SCENES))
+@pytest.mark.parametrize("min_per_tri,requested", [(3, 0), (0, 5000), (1, 20011)])
+def test_sampling_bit_exact(api, name, min_per_tri, requested):
+    scene, blockers = SCENES[name]
+    orc = Oracle(scene, blockers)
+    ototal, oper = orc.distribute_samples(min_per_tri, requested)
+    osb = orc.sample_instances(oper, min_per_tri)
+    with api.Baker() as bk:
+        bk.set_scene(scene, blockers)
+        total, per = bk.distribute_samples(min_per_tri, requested)
+        assert total == ototal
+        assert np.array_equal(per, oper)
+        sb = bk.sample_instances(per, min_per_tri)
+    assert_samples_equal(sb, osb)
+
+
+@pytest.mark.parametrize("name", list(SCENES))
+@pytest.mark.parametrize("rays", [16, 64])
+def test_rays_bit_exact(api, name, rays):
+    scene, blockers = SCENES[name]
+    off, maxd = scenes.default_distances(scene)
+    orc = Oracle(scene, blockers)
+    _, per = orc.distribute_samples(1, 0)
+    osb = orc.sample_instances(per, 1)
+    n = min(osb.n, 4000)
+    with api.Baker() as bk:
+        bk.set_scene(scene, blockers)
+        bk.set_samples(osb, per)
+        got = bk.dump_rays(0, n, rays, off, maxd)
+    want = orc.generate_rays(osb, 0, n, rays, off, maxd)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def check_hits(orc, rays, got, want):
+    mism = np.nonzero(got != want)[0]
+    agree = 1.0 - len(mism) / max(len(rays), 1)
+    assert agree >= HIT_AGREEMENT, f"agreement {agree}"
+    if len(mism):
+        m = orc.ray_margin(rays[mism])
+        assert (m <= EDGE_MARGIN).all(), f"disagreeing rays are not edge cases: margins {m[:10]}"
+    return agree
+
+
+@pytest.mark.parametrize("name", list(SCENES))
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_trace_rays_parity(api, name, mode):
+    scene, blockers = SCENES[name]
+    off, maxd = scenes.default_distances(scene)
+    orc = Oracle(scene, blockers, mode)
+    _, per = orc.distribute_samples(1, 0)
+    osb = orc.sample_instances(per, 1)
+    rng = np.random.default_rng(7)
+    pick = np.sort(rng.choice(osb.n, size=min(osb.n, 2500), replace=False))
+    rays = np.concatenate([orc.generate_rays(osb, int(g), int(g) + 1, 16, off, maxd).reshape(-1, 8) for g in pick])
+    lo, hi = scene.world_bbox()
+    ext = float((hi - lo).max())
+    rnd = np.zeros((30000, 8), dtype=np.float32)
+    rnd[:, 0:3] = rng.uniform(lo - 0.2 * ext, hi + 0.2 * ext, (30000, 3))
+    d = rng.normal(size=(30000, 3))
+    rnd[:, 4:7] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    rnd[:, 3] = rng.uniform(0, 0.01 * ext, 30000)
+    rnd[:, 7] = rng.uniform(0.05 * ext, 3 * ext, 30000)
+    # axis-aligned and degenerate directions exercise the zero-component paths
+    ax = np.zeros((600, 8), dtype=np.float32)
+    ax[:, 0:3] = rng.uniform(lo, hi, (600, 3))
+    ax[np.arange(600), 4 + (np.arange(600) % 3)] = np.where(np.arange(600) % 2, 1.0, -1.0)
+    ax[:, 7] = 10 * ext
+    rays = np.ascontiguousarray(np.concatenate([rays, rnd, ax]), dtype=np.float32)
+    want = orc.trace_rays(rays)
+    with api.Baker(instancing_mode=mode) as bk:
+        bk.set_scene(scene, blockers)
+        assert bool(bk.stats().two_level) == orc.is_two_level()
+        got = bk.trace_rays(rays)
+    assert 0.02 < want.mean() < 0.98
+    check_hits(orc, rays, got, want)
+
+
+@pytest.mark.parametrize("name", list(SCENES))
+@pytest.mark.parametrize("trace_kernel", [0, 1])
+def test_compute_ao_and_vertex_maps(api, name, trace_kernel):
+    scene, blockers = SCENES[name]
+    off, maxd = scenes.default_distances(scene)
+    rays = 64
+    orc = Oracle(scene, blockers)
+    with api.Baker(trace_kernel=trace_kernel, collect_stats=True) as bk:
+        bk.set_scene(scene, blockers)
+        total, per = bk.distribute_samples(2, 0)
+        sb = bk.sample_instances(per, 2)
+        ao = bk.compute_ao(rays, off, maxd)
+        hits = bk.hit_counts()
+        st = bk.stats()
+        assert st.rays == total * rays and st.node_visits > 0
+        v_area = bk.map_ao_to_vertices(api.FILTER_AREA_BASED)
+        v_ls = bk.map_ao_to_vertices(api.FILTER_LEAST_SQUARES, 0.1)
+        # sharded ranges reproduce the full result bit for bit (multi-GPU contract)
+        cut = total // 3
+        a0 = bk.compute_ao(rays, off, maxd, begin=0, end=cut)
+        a1 = bk.compute_ao(rays, off, maxd, begin=cut, end=total)
+        assert np.array_equal(np.concatenate([a0, a1]).view(np.uint32), ao.view(np.uint32))
+    oao, ohits = orc.compute_ao(sb, rays, off, maxd)
+    diff_rays = np.abs(hits.astype(np.int64) - ohits.astype(np.int64)).sum()
+    assert 1.0 - diff_rays / (total * rays) >= HIT_AGREEMENT
+    assert np.abs(ao - oao).max() <= 2.0 / rays
+    same = hits == ohits
+    assert np.array_equal(ao[same].view(np.uint32), oao[same].view(np.uint32))
+    o_area = orc.filter_area(sb, ao, per)
+    o_ls = orc.filter_least_squares(sb, ao, 0.1, per_instance=per)
+    for i in range(len(scene.instances)):
+        assert np.abs(v_area[i] - o_area[i]).max() <= VERTEX_AO_TOL
+        assert np.abs(v_ls[i] - o_ls[i]).max() <= VERTEX_AO_TOL
+
+
+def test_analytic_sphere_over_plane(api):
+    """Known answer, no oracle: a convex body over an (effectively) infinite plane has
+    AO(n) = (1 + n.up) / 2."""
+    scene, _ = scenes.config1_sphere(40, 40)
+    blockers = scenes.ground_blockers(scene, 1, 1.0e6, 0.03)
+    with api.Baker() as bk:
+        bk.set_scene(scene, blockers)
+        total, per = bk.distribute_samples(3, 0)
+        sb = bk.sample_instances(per, 3)
+        ao = bk.compute_ao(1024, 0.02, 1.0e7)
+    expect = (1.0 + sb.normals[:, 1]) / 2.0
+    assert np.abs(ao - expect).mean() < 5e-3
+    assert np.abs(ao - expect).max() < 6e-2
+
+
+def test_closed_box_is_fully_occluded_and_lone_triangle_is_open(api):
+    # inward-facing unit cube: every ray from an inside face hits another face
+    v = np.array([[x, y, z] for x in (0, 1) for y in (0, 1) for z in (0, 1)], dtype=np.float32)
+    quads = [(0, 1, 3, 2), (4, 6, 7, 5), (0, 4, 5, 1), (2, 3, 7, 6), (0, 2, 6, 4), (1, 5, 7, 3)]
+    tris = []
+    for a, b, c, d in quads:
+        tris += [[a, b, c], [a, c, d]]
+    tris = np.array(tris, dtype=np.uint32)
+    center = np.array([0.5, 0.5, 0.5], dtype=np.float32)
+    for t in tris:  # orient inward
+        n = np.cross(v[t[1]] - v[t[0]], v[t[2]] - v[t[0]])
+        if np.dot(n, center - v[t[0]]) < 0:
+            t[1], t[2] = t[2], t[1]
+    box = Scene([Mesh(v, tris)], [Instance(0)])
+    with api.Baker() as bk:
+        bk.set_scene(box)
+        total, per = bk.distribute_samples(8, 0)
+        bk.sample_instances(per, 8, download=False)
+        ao = bk.compute_ao(64, 1e-3, 100.0)
+    assert np.all(ao == 0.0)
+    tri = Scene([Mesh(np.array([[0, 0, 0], [1, 0, 0], [0, 0, 1]], dtype=np.float32), np.array([[0, 2, 1]], dtype=np.uint32))],
+                [Instance(0)])
+    with api.Baker() as bk:
+        bk.set_scene(tri)
+        total, per = bk.distribute_samples(16, 0)
+        bk.sample_instances(per, 16, download=False)
+        ao = bk.compute_ao(64, 1e-3, 100.0)
+        v_area = bk.map_ao_to_vertices(api.FILTER_AREA_BASED)
+    assert np.all(ao == 1.0) and np.allclose(v_area[0], 1.0)
+
+
+def test_edge_cases(api):
+    scene, blockers = SCENES["sphere_ground"]
+    with api.Baker() as bk:
+        with pytest.raises(api.AoBakeError):
+            bk.compute_ao(64, 0.1, 1.0)           # no scene yet
+        bk.set_scene(scene, Scene([], []))        # empty blockers
+        total, per = bk.distribute_samples(0, 0)  # zero samples
+        assert total == 0
+        sb = bk.sample_instances(per, 0)
+        assert sb.n == 0
+        assert bk.compute_ao(64, 0.1, 1.0).size == 0
+        with pytest.raises(api.AoBakeError):
+            bk.sample_instances([1], 3)           # below the per-face minimum
+        with pytest.raises(api.AoBakeError):
+            bk.compute_ao(0, 0.1, 1.0)
+    # an empty scene with only a blocker, and a degenerate (zero-area) triangle
+    v = np.array([[0, 0, 0], [1, 0, 0], [2, 0, 0], [0, 1, 0]], dtype=np.float32)
+    deg = Scene([Mesh(v, np.array([[0, 1, 2], [0, 1, 3]], dtype=np.uint32))], [Instance(0)])
+    orc = Oracle(deg)
+    with api.Baker() as bk:
+        bk.set_scene(deg)
+        total, per = bk.distribute_samples(2, 7)
+        ototal, oper = orc.distribute_samples(2, 7)
+        assert total == ototal == 7 and np.array_equal(per, oper)
+        sb = bk.sample_instances(per, 2)
+        osb = orc.sample_instances(oper, 2)
+        assert np.array_equal(sb.infos["tri_idx"], osb.infos["tri_idx"])
+        ao = bk.compute_ao(16, 1e-3, 10.0)
+        assert np.isfinite(ao).all()
+
+
+def test_strided_vertices(api):
+    scene, blockers = SCENES["sphere_ground"]
+    m = scene.meshes[0]
+    wide = np.zeros((len(m.vertices), 8), dtype=np.float32)
+    wide[:, 0:3] = m.vertices
+    wide[:, 4:7] = m.normals
+    strided = Scene([Mesh.__new__(Mesh)], [Instance(0)])
+    sm = strided.meshes[0]
+    sm.vertices, sm.normals, sm.tris = wide[:, 0:3], wide[:, 4:7], m.tris  # views with a 32-byte stride
+    with api.Baker() as a, api.Baker() as b:
+        a.set_scene(scene, blockers)
+        b.set_scene(strided, blockers)
+        ta, pa = a.distribute_samples(1, 0)
+        tb, pb = b.distribute_samples(1, 0)
+        assert_samples_equal(a.sample_instances(pa, 1), b.sample_instances(pb, 1))

@@ -1,0 +1,247 @@
+"""CPU tests of the oracle (the checker): golden vectors, analytic known answers, brute-force
+cross-checks, and the host-emulated kernel bodies against it.  No GPU needed."""
+import ctypes as C
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from optix_prime_baking_b200 import scenes
+from optix_prime_baking_b200.scenes import Instance, Mesh, Scene
+
+from . import oracle_binding as ob
+from .oracle_binding import Oracle
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = os.path.join(HERE, "golden", "oracle_golden.json")
+
+
+@pytest.fixture(scope="module")
+def golden():
+    with open(GOLDEN) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    subprocess.run(["make", "-s", "-C", os.path.join(HERE, "emu")], check=True)
+    E = C.CDLL(os.path.join(HERE, "emu", "libaob_emu.so"))
+    E.emu_bvh_create_flat.restype = C.c_void_p
+    E.emu_bvh_create_flat.argtypes = [C.c_void_p, C.c_uint32]
+    E.emu_bvh_create_two_level.restype = C.c_void_p
+    E.emu_bvh_create_two_level.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+    E.emu_bvh_destroy.argtypes = [C.c_void_p]
+    E.emu_trace.restype = C.c_uint64
+    E.emu_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    E.emu_generate_rays.argtypes = [C.c_void_p] * 3 + [C.c_uint64, C.c_uint64, C.c_int, C.c_float, C.c_float, C.c_void_p]
+    E.emu_tea.restype = C.c_uint32
+    E.emu_tea.argtypes = [C.c_uint32] * 3
+    E.emu_halton.restype = C.c_float
+    E.emu_halton.argtypes = [C.c_uint32] * 2
+    E.emu_sincos2pi.argtypes = [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    return E
+
+
+def test_rng_golden(golden):
+    for rounds, v0, v1, want in golden["tea"]:
+        assert ob.tea(rounds, v0, v1) == int(want, 16)
+        assert int(scenes.tea(rounds, np.uint32(v0), np.uint32(v1))) == int(want, 16)
+    for seed, stream in golden["lcg"]:
+        assert ob.lcg_stream(seed, len(stream)) == [int(x, 16) for x in stream]
+    for i, base, want in golden["halton"]:
+        assert np.float32(ob.halton(i, base)).view(np.uint32) == int(want, 16)
+
+
+def test_rng_properties():
+    # lcg low 24 bits; rnd in [0,1); halton(1,2)=0.5, halton(2,2)=0.25, halton(1,3)=1/3
+    assert all(0 <= x < (1 << 24) for x in ob.lcg_stream(12345, 1000))
+    assert ob.halton(1, 2) == 0.5 and ob.halton(2, 2) == 0.25 and ob.halton(3, 2) == 0.75
+    assert abs(ob.halton(1, 3) - 1 / 3) < 1e-7
+    for u in np.linspace(0, 0.999, 257, dtype=np.float32):
+        c, s = ob.sincos2pi(float(u))
+        assert abs(c - np.cos(2 * np.pi * float(u))) < 1e-6 and abs(s - np.sin(2 * np.pi * float(u))) < 1e-6
+
+
+def test_sample_budget_rules():
+    scene, _ = scenes.config3_bigmesh(40, seed=3)
+    orc = Oracle(scene)
+    nT = scene.num_triangles
+    for mn, req in [(3, 0), (0, 1000), (1, 10007), (2, 1)]:
+        total, per = orc.distribute_samples(mn, req)
+        assert total == max(req, mn * nT) and per.sum() == total
+        counts = orc.triangle_counts(0, total, mn)
+        assert counts.sum() == total and counts.min() >= mn
+        sb = orc.sample_instances(per, mn)
+        assert np.array_equal(np.bincount(sb.infos["tri_idx"], minlength=nT), counts)
+        b = sb.infos["bary"]
+        assert (b >= -1e-7).all() and np.allclose(b.sum(axis=1), 1.0, atol=1e-6)
+        # sum of dA over a triangle = its area
+        area = np.bincount(sb.infos["tri_idx"], weights=sb.infos["dA"].astype(np.float64), minlength=nT)
+        m = scene.meshes[0]
+        v = m.vertices.astype(np.float64)
+        ta = 0.5 * np.linalg.norm(np.cross(v[m.tris[:, 1]] - v[m.tris[:, 0]], v[m.tris[:, 2]] - v[m.tris[:, 0]]), axis=1)
+        assert np.allclose(area[counts > 0], ta[counts > 0], rtol=1e-5)
+    # leftover rule with equal areas and < 1 sample per triangle: the first N triangles get one each
+    flat = Scene([scenes.heightfield(8, seed=1, height=0.0)], [Instance(0)])
+    o2 = Oracle(flat)
+    counts = o2.triangle_counts(0, 50, 0)
+    assert counts.sum() == 50 and set(counts.tolist()) <= {0, 1}
+
+
+def test_cosine_law_and_hemisphere():
+    scene, blk = scenes.config1_sphere(24, 24)
+    orc = Oracle(scene, blk)
+    _, per = orc.distribute_samples(1, 0)
+    sb = orc.sample_instances(per, 1)
+    rays = orc.generate_rays(sb, 0, sb.n, 256, 0.02, 20.0)
+    d = rays[:, :, 4:7]
+    assert np.abs(np.linalg.norm(d, axis=2) - 1).max() < 1e-5
+    cosn = (d * sb.normals[:, None, :]).sum(axis=2)
+    assert abs(cosn.mean() - 2.0 / 3.0) < 2e-3          # E[cos] = 2/3 under cosine sampling
+    assert ((d * sb.face_normals[:, None, :]).sum(axis=2) > 0).mean() > 0.999
+    o = rays[:, 0, 0:3]
+    assert np.allclose(o, sb.positions + np.float32(0.02) * sb.normals, atol=1e-6)
+
+
+def test_analytic_ao_sphere_over_plane():
+    scene, _ = scenes.config1_sphere(40, 40)
+    blockers = scenes.ground_blockers(scene, 1, 1.0e6, 0.03)
+    orc = Oracle(scene, blockers)
+    _, per = orc.distribute_samples(3, 0)
+    sb = orc.sample_instances(per, 3)
+    ao, _ = orc.compute_ao(sb, 1024, 0.02, 1.0e7)
+    expect = (1.0 + sb.normals[:, 1]) / 2.0
+    assert np.abs(ao - expect).mean() < 5e-3 and np.abs(ao - expect).max() < 6e-2
+
+
+def _random_rays(scene, n, seed):
+    rng = np.random.default_rng(seed)
+    lo, hi = scene.world_bbox()
+    ext = float((hi - lo).max())
+    r = np.zeros((n, 8), dtype=np.float32)
+    r[:, 0:3] = rng.uniform(lo - 0.2 * ext, hi + 0.2 * ext, (n, 3))
+    d = rng.normal(size=(n, 3))
+    r[:, 4:7] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    r[:, 7] = rng.uniform(0.05 * ext, 3 * ext, n)
+    return r
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_oracle_bvh_vs_brute_force(mode):
+    scene, blk = scenes.config4_instanced(grid=2, stacks=10, slices=10, with_ground=True)
+    orc = Oracle(scene, blk, mode)
+    rays = _random_rays(scene, 20000, 3)
+    a, b = orc.trace_rays(rays), orc.trace_rays(rays, brute=True)
+    assert np.array_equal(a, b) and 0.02 < a.mean() < 0.98
+
+
+def _world_tris(scene_list):
+    out = []
+    for sc in scene_list:
+        for inst in sc.instances:
+            m = sc.meshes[inst.mesh_index]
+            v, xf = m.vertices, inst.xform.astype(np.float32)
+            w = np.empty_like(v)
+            for r in range(3):
+                w[:, r] = ((xf[r, 0] * v[:, 0] + xf[r, 1] * v[:, 1]) + xf[r, 2] * v[:, 2]) + xf[r, 3]
+            out.append(w[m.tris].reshape(-1, 9))
+    return np.ascontiguousarray(np.concatenate(out), dtype=np.float32)
+
+
+def test_emulated_kernels_match_oracle(emu):
+    """The LBVH build, 8-wide collapse, quantised traversal and ray generation that the CUDA
+    kernels run, executed serially on the CPU, agree with the oracle."""
+    for rounds, v0, v1 in [(2, 1, 2), (4, 0, 0), (4, 123, 456789)]:
+        assert emu.emu_tea(rounds, v0, v1) == ob.tea(rounds, v0, v1)
+    for i in range(1, 200):
+        assert emu.emu_halton(i, 2) == ob.halton(i, 2) and emu.emu_halton(i, 3) == ob.halton(i, 3)
+    for name, (scene, blk) in {"sphere": scenes.config1_sphere(30, 30), "hf": scenes.config2_heightfield(40)}.items():
+        orc = Oracle(scene, blk)
+        _, per = orc.distribute_samples(1, 0)
+        sb = orc.sample_instances(per, 1)
+        off, md = scenes.default_distances(scene)
+        n = min(sb.n, 1500)
+        want = orc.generate_rays(sb, 0, n, 16, off, md)
+        got = np.zeros_like(want)
+        emu.emu_generate_rays(sb.positions.ctypes.data, sb.normals.ctypes.data, sb.face_normals.ctypes.data, 0, n, 16,
+                              float(off), float(md), got.ctypes.data)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), name
+        rays = np.ascontiguousarray(np.concatenate([want.reshape(-1, 8), _random_rays(scene, 8000, 1)]), dtype=np.float32)
+        wt = _world_tris([scene, blk])
+        B = emu.emu_bvh_create_flat(wt.ctypes.data, len(wt))
+        hit = np.zeros(len(rays), dtype=np.uint8)
+        emu.emu_trace(B, rays.ctypes.data, len(rays), hit.ctypes.data, None)
+        emu.emu_bvh_destroy(B)
+        assert np.array_equal(hit, orc.trace_rays(rays)), name
+
+
+def test_emulated_two_level_matches_oracle(emu):
+    scene, blk = scenes.config4_instanced(grid=2, stacks=10, slices=10, with_ground=True)
+    orc = Oracle(scene, blk, 2)
+    meshes = [m for m in scene.meshes] + [m for m in blk.meshes]
+    soups = [np.ascontiguousarray(m.vertices[m.tris].reshape(-1, 9), dtype=np.float32) for m in meshes]
+    ptrs = (C.c_void_p * len(soups))(*[s.ctypes.data for s in soups])
+    ntris = np.array([len(s) for s in soups], dtype=np.uint32)
+    insts = [(i.mesh_index, i.xform) for i in scene.instances] + [(len(scene.meshes) + i.mesh_index, i.xform) for i in blk.instances]
+    imesh = np.array([m for m, _ in insts], dtype=np.uint32)
+    xf = np.ascontiguousarray(np.stack([x for _, x in insts]), dtype=np.float32).reshape(-1, 16)
+    inv = np.zeros((len(insts), 12), dtype=np.float32)
+    for k in range(len(insts)):
+        ob.lib().ao_oracle_affine_inverse(xf[k].ctypes.data, inv[k].ctypes.data)
+    B = emu.emu_bvh_create_two_level(len(soups), ptrs, ntris.ctypes.data, len(insts), imesh.ctypes.data, xf.ctypes.data, inv.ctypes.data)
+    rays = _random_rays(scene, 20000, 5)
+    hit = np.zeros(len(rays), dtype=np.uint8)
+    emu.emu_trace(B, rays.ctypes.data, len(rays), hit.ctypes.data, None)
+    emu.emu_bvh_destroy(B)
+    want = orc.trace_rays(rays)
+    assert (hit != want).mean() <= 1e-4 and 0.02 < want.mean() < 0.98
+
+
+def test_area_filter_properties():
+    scene, blk = scenes.config1_sphere(16, 16)
+    orc = Oracle(scene, blk)
+    _, per = orc.distribute_samples(4, 0)
+    sb = orc.sample_instances(per, 4)
+    const = orc.filter_area(sb, np.full(sb.n, 0.37, dtype=np.float32))[0]
+    assert np.allclose(const, 0.37, atol=1e-6)           # partition of unity
+    ao, _ = orc.compute_ao(sb, 64, 0.02, 20.0)
+    v = orc.filter_area(sb, ao)[0]
+    assert v.min() >= ao.min() - 1e-6 and v.max() <= ao.max() + 1e-6
+
+
+def test_least_squares_filter_algebra():
+    """w = 0 and AO exactly linear in the barycentrics returns the generating vertex values; a
+    linear field on a planar mesh is in the regulariser's null space."""
+    flat = Scene([scenes.heightfield(12, seed=2, height=0.0)], [Instance(0)])
+    m = flat.meshes[0]
+    orc = Oracle(flat)
+    _, per = orc.distribute_samples(6, 0)
+    sb = orc.sample_instances(per, 6)
+    rng = np.random.default_rng(0)
+    xv = rng.uniform(0, 1, len(m.vertices)).astype(np.float32)
+    tri = m.tris[sb.infos["tri_idx"]]
+    ao = (sb.infos["bary"] * xv[tri]).sum(axis=1).astype(np.float32)
+    got = orc.filter_least_squares(sb, ao, weight=0.0, tol=1e-12)[0]
+    assert np.abs(got - xv).max() < 1e-4
+    lin = (0.2 + 0.03 * m.vertices[:, 0] - 0.05 * m.vertices[:, 2]).astype(np.float32)
+    ao_lin = (sb.infos["bary"] * lin[tri]).sum(axis=1).astype(np.float32)
+    got = orc.filter_least_squares(sb, ao_lin, weight=10.0, tol=1e-12)[0]
+    assert np.abs(got - lin).max() < 1e-4                # R x = 0 for linear x, so the fit is exact
+    # regularisation pulls a noisy field towards smoothness but keeps its mean
+    noisy = (0.5 + 0.2 * rng.standard_normal(sb.n)).astype(np.float32)
+    a, b = orc.filter_least_squares(sb, noisy, 0.0)[0], orc.filter_least_squares(sb, noisy, 1.0)[0]
+    assert np.var(b) < np.var(a) and abs(a.mean() - b.mean()) < 0.02
+
+
+def test_ground_plane_matches_host_helper():
+    lo, hi = np.array([-1, -1, -1], dtype=np.float32), np.array([1, 2, 3], dtype=np.float32)
+    for up in range(6):
+        v = np.zeros((4, 3), dtype=np.float32)
+        t = np.zeros((2, 3), dtype=np.uint32)
+        ob.lib().ao_oracle_make_ground_plane(lo.ctypes.data, hi.ctypes.data, up, 100.0, 0.03, v.ctypes.data, t.ctypes.data)
+        g = scenes.ground_plane(lo, hi, up, 100.0, 0.03)
+        assert np.allclose(v, g.vertices) and np.array_equal(t, g.tris)
+        n = np.cross(v[t[0, 1]] - v[t[0, 0]], v[t[0, 2]] - v[t[0, 0]])
+        assert (n[up % 3] > 0) == (up < 3)               # faces the scene
