@@ -114,7 +114,8 @@ typedef struct AoBakeParams {
   float   cg_tolerance;           /* relative residual */
   int32_t trace_kernel;           /* 0 = default (persistent, refilling); 1 = simple one-ray-per-thread */
   int32_t collect_stats;          /* 1: count node visits / triangle tests in aobake_compute_ao */
-  int32_t reserved[8];
+  int32_t refill_below;           /* persistent kernel: refill a warp when fewer lanes are traversing (0 = default 24) */
+  int32_t reserved[7];
 } AoBakeParams;
 
 typedef struct AoTimings {        /* milliseconds, device-timed with CUDA events unless noted */
@@ -126,7 +127,8 @@ typedef struct AoTimings {        /* milliseconds, device-timed with CUDA events
   float host_total_ms;            /* wall clock of the last API call */
   uint64_t rays_traced;           /* last compute_ao */
   int32_t cg_iterations;          /* last least-squares solve (sum over instances) */
-  int32_t reserved[7];
+  int32_t kernel_launches;        /* kernels launched inside the last compute_ao's timed region */
+  int32_t reserved[6];
 } AoTimings;
 
 typedef struct AoStats {

@@ -37,13 +37,14 @@ EXPORTS = [
 class AoBakeParams(C.Structure):
     _fields_ = [("device", C.c_int32), ("instancing_mode", C.c_int32), ("cg_max_iterations", C.c_int32),
                 ("cg_tolerance", C.c_float), ("trace_kernel", C.c_int32), ("collect_stats", C.c_int32),
-                ("reserved", C.c_int32 * 8)]
+                ("refill_below", C.c_int32), ("reserved", C.c_int32 * 7)]
 
 
 class AoTimings(C.Structure):
     _fields_ = [("upload_ms", C.c_float), ("bvh_build_ms", C.c_float), ("sample_ms", C.c_float),
                 ("trace_ms", C.c_float), ("filter_ms", C.c_float), ("host_total_ms", C.c_float),
-                ("rays_traced", C.c_uint64), ("cg_iterations", C.c_int32), ("reserved", C.c_int32 * 7)]
+                ("rays_traced", C.c_uint64), ("cg_iterations", C.c_int32), ("kernel_launches", C.c_int32),
+                ("reserved", C.c_int32 * 6)]
 
 
 class AoStats(C.Structure):
@@ -110,11 +111,13 @@ class Baker:
     """Resident bake context (AoBake*)."""
 
     def __init__(self, device: int = 0, instancing_mode: int = INSTANCING_AUTO, collect_stats: bool = False,
-                 cg_tolerance: float = 1e-6, cg_max_iterations: int = 2000, trace_kernel: int = 0):
+                 cg_tolerance: float = 1e-6, cg_max_iterations: int = 2000, trace_kernel: int = 0,
+                 refill_below: int = 0):
         self.lib = load_library()
         p = default_params()
         p.device, p.instancing_mode, p.collect_stats = device, instancing_mode, int(collect_stats)
         p.cg_tolerance, p.cg_max_iterations, p.trace_kernel = cg_tolerance, cg_max_iterations, trace_kernel
+        p.refill_below = refill_below
         self._h = C.c_void_p()
         rc = self.lib.aobake_create(C.byref(p), C.byref(self._h))
         if rc != 0:

@@ -331,64 +331,84 @@ struct RayState {
   V3 org, dir;
   float tmin, tmax;
   V3 idir;     // clamped reciprocal for the slab tests
-  Shear sh;
 };
-AOB_HD float safe_rcp(float d) {
+AOB_HD float safe_rcp(float d) {  // for the slab tests only; their padding absorbs 2 ulp here
   const float tiny = 1e-18f;
   float a = fabsf(d) > tiny ? d : (d < 0.0f ? -tiny : tiny);
+#if defined(__CUDA_ARCH__)
+  return __frcp_rn(a);
+#else
   return 1.0f / a;
+#endif
 }
 AOB_HD void ray_setup(RayState& r, V3 org, V3 dir, float tmin, float tmax) {
   r.org = org; r.dir = dir; r.tmin = tmin; r.tmax = tmax;
   r.idir = v3(safe_rcp(dir.x), safe_rcp(dir.y), safe_rcp(dir.z));
-  r.sh = make_shear(dir);
 }
 
-AOB_D float q2f(uint32_t word, int k) {  // 32768 + byte k of word, as float (no int->float convert)
-  return as_float(byte_perm(word, 0x47000000u, 0x7404u | ((uint32_t)k << 4)));
+AOB_D float q2f(uint32_t word, int k, uint32_t k47 = 0x47000000u) {  // 32768 + byte k of word, as float (no int->float convert)
+  return as_float(byte_perm(word, k47, 0x7404u | ((uint32_t)k << 4)));
 }
 
 // Slab-tests the 8 quantised child boxes of node `idx`; returns the hit mask in the layout
 // [31:24] internal slots | [23:0] leaf primitive bits.
+//
+// Conservative slabs: t(q) = (32768 + q) * ad + o with o = b - 32768 * ad, b = (p - org) * idir,
+// ad = 2^e * idir; the byte q is dropped into the mantissa of 32768.0f with one PRMT (no
+// int->float conversion).  Rounding of b (incl. an approximate reciprocal), of the folded
+// constant o and of the final FMA is bounded by 5e-7*|b| + 0.008*|ad|; near/far are pushed
+// apart by pad = 1e-6*|b| + 0.0234*|ad| (2.3 % of one quantisation step), so a box the exact
+// ray touches is never culled and no per-child padding multiply is needed.
 AOB_D uint32_t intersect_node8(const U4* nodes, uint32_t idx, const RayState& r, uint32_t* child_base,
                                uint32_t* prim_base, uint32_t* imask) {
   const U4* p = nodes + 5ull * idx;
   const U4 n0 = ld_u4(p), n1 = ld_u4(p + 1), n2 = ld_u4(p + 2), n3 = ld_u4(p + 3), n4 = ld_u4(p + 4);
   *child_base = n1.x;
   *prim_base = n1.y;
-  *imask = n0.w >> 24;
+  const uint32_t im = n0.w >> 24;
+  *imask = im;
   const float adx = as_float((n0.w & 0xffu) << 23) * r.idir.x;
   const float ady = as_float(((n0.w >> 8) & 0xffu) << 23) * r.idir.y;
   const float adz = as_float(((n0.w >> 16) & 0xffu) << 23) * r.idir.z;
-  // t(q) = (32768 + q) * ad + (o - 32768 * ad); near/far padded by 2^-8 of a grid step, which
-  // bounds the rounding of the folded constant (see DESIGN.md "conservative slabs").
-  const float ox = (as_float(n0.x) - r.org.x) * r.idir.x - 32768.0f * adx;
-  const float oy = (as_float(n0.y) - r.org.y) * r.idir.y - 32768.0f * ady;
-  const float oz = (as_float(n0.z) - r.org.z) * r.idir.z - 32768.0f * adz;
-  const float padx = 0.00390625f * fabsf(adx), pady = 0.00390625f * fabsf(ady), padz = 0.00390625f * fabsf(adz);
+  const float bx = (as_float(n0.x) - r.org.x) * r.idir.x;
+  const float by = (as_float(n0.y) - r.org.y) * r.idir.y;
+  const float bz = (as_float(n0.z) - r.org.z) * r.idir.z;
+  const float ox = fmaf(-32768.0f, adx, bx), oy = fmaf(-32768.0f, ady, by), oz = fmaf(-32768.0f, adz, bz);
+  const float padx = fmaf(0.0234375f, fabsf(adx), 1.0e-6f * fabsf(bx));
+  const float pady = fmaf(0.0234375f, fabsf(ady), 1.0e-6f * fabsf(by));
+  const float padz = fmaf(0.0234375f, fabsf(adz), 1.0e-6f * fabsf(bz));
   const float onx = ox - padx, ofx = ox + padx, ony = oy - pady, ofy = oy + pady, onz = oz - padz, ofz = oz + padz;
   const bool nx = r.dir.x < 0.0f, ny = r.dir.y < 0.0f, nz = r.dir.z < 0.0f;
-  uint32_t hitmask = 0;
+  uint32_t hb = 0;
+  uint32_t k47 = 0x47000000u;
+#if defined(__CUDA_ARCH__)
+  asm volatile("mov.b32 %0, 0x47000000;" : "=r"(k47));  // keep the PRMT constant in one register (no re-materialising MOVs)
+#endif
 #pragma unroll
   for (int h = 0; h < 2; h++) {
     const uint32_t lox = h ? n2.y : n2.x, loy = h ? n2.w : n2.z, loz = h ? n3.y : n3.x;
     const uint32_t hix = h ? n3.w : n3.z, hiy = h ? n4.y : n4.x, hiz = h ? n4.w : n4.z;
-    const uint32_t meta = h ? n1.w : n1.z;
     const uint32_t nwx = nx ? hix : lox, fwx = nx ? lox : hix;
     const uint32_t nwy = ny ? hiy : loy, fwy = ny ? loy : hiy;
     const uint32_t nwz = nz ? hiz : loz, fwz = nz ? loz : hiz;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-      const float tnx = fmaf(q2f(nwx, k), adx, onx), tfx = fmaf(q2f(fwx, k), adx, ofx);
-      const float tny = fmaf(q2f(nwy, k), ady, ony), tfy = fmaf(q2f(fwy, k), ady, ofy);
-      const float tnz = fmaf(q2f(nwz, k), adz, onz), tfz = fmaf(q2f(fwz, k), adz, ofz);
+      const float tnx = fmaf(q2f(nwx, k, k47), adx, onx), tfx = fmaf(q2f(fwx, k, k47), adx, ofx);
+      const float tny = fmaf(q2f(nwy, k, k47), ady, ony), tfy = fmaf(q2f(fwy, k, k47), ady, ofy);
+      const float tnz = fmaf(q2f(nwz, k, k47), adz, onz), tfz = fmaf(q2f(fwz, k, k47), adz, ofz);
       const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, r.tmin));
       const float tf = fminf(fminf(tfx, tfy), fminf(tfz, r.tmax));
-      if (tn <= tf * 1.0000005f) {
-        const uint32_t m = (meta >> (8 * k)) & 0xffu;
-        hitmask |= (m >> 5) << (m & 31u);
-      }
+      if (tn <= tf) hb |= 1u << (4 * h + k);
     }
+  }
+  // expand the 8 slot bits: internal slots map to bits 24+slot; leaf slots to their primitive bits
+  uint32_t hitmask = (hb & im) << 24;
+  uint32_t lh = hb & ~im;
+  while (lh) {
+    const int s = ffs32(lh) - 1;
+    lh &= lh - 1u;
+    const uint32_t m = (((s & 4) ? n1.w : n1.z) >> (8 * (s & 3))) & 0xffu;
+    hitmask |= (m >> 5) << (m & 31u);
   }
   return hitmask;
 }
@@ -424,6 +444,10 @@ AOB_D bool trace_any_hit(const BvhView& bvh, V3 org, V3 dir, float tmin, float t
       T = G;
       G.x = 0; G.y = 0;
     }
+    // the Woop shear constants are only needed by rays that reach a triangle: computed lazily,
+    // per primitive group
+    Shear sh;
+    if (T.y && in_blas) sh = make_shear(r.dir);
     while (T.y) {
       const int b = ffs32(T.y) - 1;
       T.y &= T.y - 1u;
@@ -431,7 +455,7 @@ AOB_D bool trace_any_hit(const BvhView& bvh, V3 org, V3 dir, float tmin, float t
       if (in_blas) {
         const F4 a = ld_f4(bvh.tris + 3ull * prim), bb = ld_f4(bvh.tris + 3ull * prim + 1), c = ld_f4(bvh.tris + 3ull * prim + 2);
         if (STATS) cnt->tris++;
-        if (woop_hit(r.org, r.sh, r.tmin, r.tmax, v3(a.x, a.y, a.z), v3(bb.x, bb.y, bb.z), v3(c.x, c.y, c.z))) return true;
+        if (woop_hit(r.org, sh, r.tmin, r.tmax, v3(a.x, a.y, a.z), v3(bb.x, bb.y, bb.z), v3(c.x, c.y, c.z))) return true;
       } else {
         // instance leaf: save the TLAS continuation, switch to object space
         if (T.y) stack[sp++] = T;

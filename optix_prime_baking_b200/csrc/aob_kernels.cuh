@@ -366,6 +366,190 @@ __global__ void __launch_bounds__(256) k_ao_simple(BvhView bvh, SampleView S, ui
   }
 }
 
+// Variant 0 (default): persistent warps with per-lane ray refill.
+//   * grid = resident CTAs only (multiple of the SM count); every lane owns one work item
+//     (sample, strata chunk) at a time, fetched with a warp-aggregated atomicAdd on a global
+//     counter, and walks its strata one ray at a time;
+//   * lanes whose ray terminates go idle; when fewer than `refill_below` lanes of the warp are
+//     still traversing, the idle lanes generate their next rays together (so ray generation
+//     runs converged) and traversal resumes — the warp-level compaction/refill of north_star;
+//   * the traversal stack lives in shared memory ([depth][thread], conflict-free 8-byte
+//     columns) for the first kSmStack entries and spills to local memory beyond;
+//   * the Woop shear constants are computed lazily, only by lanes that reach a triangle.
+constexpr int kAoBlock = 128;
+constexpr int kSmStack = 12;
+
+template <bool STATS, bool TWO_LEVEL>
+__global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleView S, uint64_t begin, uint32_t n, int q, float offset,
+                                                             float maxdist, uint32_t n_chunks, uint32_t refill_below,
+                                                             uint32_t* __restrict__ hits, unsigned long long* __restrict__ counter,
+                                                             unsigned long long* __restrict__ stats) {
+  __shared__ U2 s_stack[kSmStack][kAoBlock];
+  U2 l_stack[kStackSize - kSmStack];
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const uint32_t q2 = (uint32_t)(q * q);
+  auto push = [&](int& sp, U2 v) {
+    if (sp < kSmStack) s_stack[sp][threadIdx.x] = v;
+    else l_stack[sp - kSmStack] = v;
+    sp++;
+  };
+  auto pop = [&](int& sp) -> U2 {
+    sp--;
+    return sp < kSmStack ? s_stack[sp][threadIdx.x] : l_stack[sp - kSmStack];
+  };
+
+  // per-lane item state
+  bool have_item = false, ray_active = false;
+  uint32_t rel = 0, pass = 0, pass_end = 0, nh = 0;
+  V3 org = v3(0, 0, 0), nrm = v3(0, 0, 0), fnrm = v3(0, 0, 0);
+  Onb onb;
+  onb.t = onb.b = v3(0, 0, 0);
+  // per-lane ray state
+  RayState r;
+  r.tmin = 0.0f; r.tmax = maxdist;
+  r.org = org; r.dir = org; r.idir = org;
+  V3 wdir = v3(0, 0, 0);  // world-space direction (two-level: restored after a BLAS)
+  bool in_blas = !TWO_LEVEL;
+  U2 G;
+  G.x = 0; G.y = 0;
+  int sp = 0;
+  uint32_t c_nodes = 0, c_tris = 0, c_insts = 0;
+  const unsigned long long n_blocks = ((unsigned long long)n + 31ull) / 32ull;
+  const unsigned long long total_items = n_blocks * n_chunks;  // item = (block of 32 samples, strata chunk)
+
+  while (true) {
+    // ------------------------------ refill ------------------------------
+    if (!ray_active && have_item && pass == pass_end) {
+      if (n_chunks > 1) atomicAdd(&hits[rel], nh);
+      else hits[rel] = nh;
+      have_item = false;
+    }
+    if (!__any_sync(0xffffffffu, have_item)) {
+      // the whole warp is done with its block: fetch the next (block, chunk) item.  Blocks of
+      // consecutive samples keep the warp's rays spatially coherent (samples are emitted in
+      // triangle order), chunk-major numbering keeps concurrent warps on neighbouring blocks.
+      unsigned long long w = 0;
+      if (lane == 0) w = atomicAdd(counter, 1ull);
+      w = __shfl_sync(0xffffffffu, w, 0);
+      if (w >= total_items) break;
+      const uint32_t chunk = (uint32_t)(w / n_blocks);
+      const unsigned long long blk = w - (unsigned long long)chunk * n_blocks;
+      const unsigned long long rr = blk * 32ull + lane;
+      if (rr < n) {
+        rel = (uint32_t)rr;
+        pass = (uint32_t)(((uint64_t)chunk * q2) / n_chunks);
+        pass_end = (uint32_t)(((uint64_t)(chunk + 1) * q2) / n_chunks);
+        const uint64_t g = begin + rel;
+        const V3 p = v3(S.pos[3 * g], S.pos[3 * g + 1], S.pos[3 * g + 2]);
+        nrm = v3(S.nrm[3 * g], S.nrm[3 * g + 1], S.nrm[3 * g + 2]);
+        fnrm = v3(S.fnrm[3 * g], S.fnrm[3 * g + 1], S.fnrm[3 * g + 2]);
+        onb = make_onb(nrm);
+        org = ao_ray_origin(p, nrm, offset);
+        nh = 0;
+        have_item = true;
+      }
+    }
+    if (!ray_active && have_item && pass < pass_end) {
+      wdir = ao_ray_dir((uint32_t)(begin + rel), pass, q, nrm, fnrm, onb);
+      pass++;
+      r.org = org; r.dir = wdir;
+      r.idir = v3(safe_rcp(wdir.x), safe_rcp(wdir.y), safe_rcp(wdir.z));
+      in_blas = !TWO_LEVEL;
+      G.x = bvh.root;
+      G.y = (1u << 24) | 1u;
+      sp = 0;
+      ray_active = true;
+    }
+    if (!__any_sync(0xffffffffu, ray_active)) continue;  // block finished (or empty): commit + fetch next
+
+    // ------------------------------ traverse ------------------------------
+    while (true) {
+      if (ray_active) {
+        U2 T;
+        T.x = 0; T.y = 0;
+        if (G.y & 0xff000000u) {
+          const int bit = 31 - __clz((int)G.y);
+          G.y &= ~(1u << bit);
+          const uint32_t slot = (uint32_t)bit - 24u;
+          const uint32_t node = G.x + (uint32_t)__popc(G.y & 0xffu & ((1u << slot) - 1u));
+          if (G.y & 0xff000000u) push(sp, G);
+          uint32_t cb, pb, im;
+          const uint32_t hm = intersect_node8(bvh.nodes, node, r, &cb, &pb, &im);
+          if (STATS) c_nodes++;
+          G.x = cb; G.y = (hm & 0xff000000u) | im;
+          T.x = pb; T.y = hm & 0x00ffffffu;
+        } else if (TWO_LEVEL) {
+          T = G;  // a postponed TLAS primitive group
+          G.x = 0; G.y = 0;
+        }
+        bool hit = false;
+        if (T.y) {
+          if (in_blas) {
+            const Shear sh = make_shear(r.dir);
+            do {
+              const int b = __ffs((int)T.y) - 1;
+              T.y &= T.y - 1u;
+              const uint64_t prim = (uint64_t)T.x + (uint32_t)b;
+              const F4 a = ld_f4(bvh.tris + 3 * prim), bb = ld_f4(bvh.tris + 3 * prim + 1), c = ld_f4(bvh.tris + 3 * prim + 2);
+              if (STATS) c_tris++;
+              hit = woop_hit(r.org, sh, 0.0f, maxdist, v3(a.x, a.y, a.z), v3(bb.x, bb.y, bb.z), v3(c.x, c.y, c.z));
+            } while (T.y && !hit);
+          } else if (TWO_LEVEL) {
+            // first instance of the group: save the TLAS continuation, switch to object space
+            const int b = __ffs((int)T.y) - 1;
+            T.y &= T.y - 1u;
+            const uint64_t prim = (uint64_t)T.x + (uint32_t)b;
+            if (T.y) push(sp, T);
+            if (G.y & 0xff000000u) push(sp, G);
+            U2 sen;
+            sen.x = kSentinel; sen.y = 0;
+            push(sp, sen);
+            const F4 r0 = ld_f4(bvh.insts + 4 * prim), r1 = ld_f4(bvh.insts + 4 * prim + 1), r2 = ld_f4(bvh.insts + 4 * prim + 2);
+            const F4 r3 = ld_f4(bvh.insts + 4 * prim + 3);
+            const float m[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
+            if (STATS) c_insts++;
+            r.org = xf_point(m, org);
+            r.dir = xf_vector(m, wdir);
+            r.idir = v3(safe_rcp(r.dir.x), safe_rcp(r.dir.y), safe_rcp(r.dir.z));
+            in_blas = true;
+            G.x = __float_as_uint(r3.x);
+            G.y = (1u << 24) | 1u;
+          }
+        }
+        if (hit) {
+          nh++;
+          ray_active = false;
+        } else if ((G.y & 0xff000000u) == 0u) {
+          while (true) {
+            if (sp == 0) { ray_active = false; break; }
+            G = pop(sp);
+            if (TWO_LEVEL && G.x == kSentinel && G.y == 0u) {
+              r.org = org; r.dir = wdir;
+              r.idir = v3(safe_rcp(wdir.x), safe_rcp(wdir.y), safe_rcp(wdir.z));
+              in_blas = false;
+              continue;
+            }
+            break;
+          }
+        }
+      }
+      const uint32_t act = __ballot_sync(0xffffffffu, ray_active);
+      if (act == 0u) break;
+      if ((uint32_t)__popc(act) < refill_below) {
+        // leave only if some idle lane can actually take a new ray
+        const bool can = !ray_active && have_item && pass < pass_end;
+        if (__any_sync(0xffffffffu, can)) break;
+      }
+    }
+  }
+  if (STATS) {
+    atomicAdd(&stats[0], (unsigned long long)c_nodes);
+    atomicAdd(&stats[1], (unsigned long long)c_tris);
+    atomicAdd(&stats[2], (unsigned long long)c_insts);
+  }
+}
+
 __global__ void k_ao_finalize(const uint32_t* __restrict__ hits, uint64_t n, float denom, float* __restrict__ ao) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;

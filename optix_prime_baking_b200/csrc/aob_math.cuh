@@ -107,7 +107,8 @@ AOB_HD uint32_t lcg(uint32_t& s) {
   s = 1664525u * s + 1013904223u;
   return s & 0x00FFFFFFu;
 }
-AOB_HD float rnd(uint32_t& s) { return ex::div((float)lcg(s), 16777216.0f); }
+// lcg / 2^24: the division by a power of two is exact, so the multiply is bit-identical
+AOB_HD float rnd(uint32_t& s) { return ex::mul((float)lcg(s), 5.9604644775390625e-8f); }
 
 // radical inverse, fp32 accumulate (bake_sample.cpp; decision #4)
 AOB_HD float halton(uint32_t i, uint32_t base) {
@@ -175,8 +176,13 @@ AOB_HD V3 cosine_dir(float u0, float u1, V3 n, const Onb& o) {
 AOB_HD V3 ao_ray_dir(uint32_t g, uint32_t pass, int q, V3 n, V3 fn, const Onb& onb) {
   const uint32_t px = pass / (uint32_t)q, py = pass - px * (uint32_t)q;
   uint32_t seed = tea<2>((pass << 16) | pass, g);
-  float u0 = ex::div(ex::add((float)px, rnd(seed)), (float)q);
-  float u1 = ex::div(ex::add((float)py, rnd(seed)), (float)q);
+  // (p + rnd) / q: for power-of-two q (all BASELINE configs) the reciprocal is exact and the
+  // multiply is bit-identical to the IEEE division; other q take the division.
+  const bool pow2 = (q & (q - 1)) == 0;
+  const float fq = (float)q, rq = ex::div(1.0f, fq);
+  const float s0 = ex::add((float)px, rnd(seed)), s1 = ex::add((float)py, rnd(seed));
+  float u0 = pow2 ? ex::mul(s0, rq) : ex::div(s0, fq);
+  float u1 = pow2 ? ex::mul(s1, rq) : ex::div(s1, fq);
   V3 d = v3(0.f, 0.f, 0.f);
   for (int attempt = 0; attempt < 5; attempt++) {
     d = cosine_dir(u0, u1, n, onb);

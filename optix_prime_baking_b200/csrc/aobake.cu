@@ -128,6 +128,7 @@ struct AoBake {
   DBuf<float> d_ao;
   DBuf<uint32_t> d_hits;
   DBuf<unsigned long long> d_stats;
+  DBuf<unsigned long long> d_counter;
   bool have_ao = false;
 
   AoTimings timings{};
@@ -349,6 +350,7 @@ int aobake_default_params(AoBakeParams* p) {
   p->cg_tolerance = 1e-6f;
   p->trace_kernel = 0;
   p->collect_stats = 0;
+  p->refill_below = 0;
   return AOBAKE_OK;
 }
 
@@ -380,7 +382,7 @@ int aobake_create(const AoBakeParams* params, AoBake** out) {
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, p.device);
   if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
-      ctx->d_stats.alloc(4) != cudaSuccess) {
+      ctx->d_stats.alloc(4) != cudaSuccess || ctx->d_counter.alloc(1) != cudaSuccess) {
     g_create_error = std::string("context setup: ") + cudaGetErrorString(cudaGetLastError());
     delete ctx;
     return AOBAKE_ERR_CUDA;
@@ -754,12 +756,14 @@ int aobake_compute_ao_range(AoBake* ctx, size_t begin, size_t end, int rays_per_
   const BvhView bvh = bvh_view(ctx);
   if (stats) CK(cudaMemsetAsync(ctx->d_stats.p, 0, 4 * sizeof(unsigned long long), st));
   CK(cudaEventRecord(ctx->ev0, st));
-  {
+  const uint32_t q2 = (uint32_t)(q * q);
+  int launches = 0;
+  if (ctx->params.trace_kernel == 1) {
     // simple variant: enough (sample block, strata chunk) items to fill the machine
     const uint64_t n_blocks = (n + 31) / 32;
     const uint64_t want = (uint64_t)ctx->sm_count * 64ull * 4ull;
     uint32_t n_chunks = 1;
-    while (n_blocks * n_chunks < want && n_chunks * 2 <= (uint32_t)(q * q)) n_chunks *= 2;
+    while (n_blocks * n_chunks < want && n_chunks * 2 <= q2) n_chunks *= 2;
     if (n_chunks > 1) CK(cudaMemsetAsync(ctx->d_hits.p + begin, 0, n * sizeof(uint32_t), st));
     const uint64_t warps = n_blocks * n_chunks;
     const unsigned grid = grid_for(warps * 32, 256);
@@ -768,9 +772,35 @@ int aobake_compute_ao_range(AoBake* ctx, size_t begin, size_t end, int rays_per_
     else
       k_ao_simple<false><<<grid, 256, 0, st>>>(bvh, S, begin, end, q, offset, maxdist, n_chunks, ctx->d_hits.p + begin, ctx->d_stats.p);
     CKL();
+    launches++;
+  } else {
+    // persistent variant: one resident wave of CTAs (a multiple of the SM count), dynamic work fetch
+    if (n > 0xfffffff0ull) return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "more than 2^32 samples in one range");
+    using KernelT = void (*)(BvhView, SampleView, uint64_t, uint32_t, int, float, float, uint32_t, uint32_t, uint32_t*, unsigned long long*,
+                             unsigned long long*);
+    KernelT kern = ctx->two_level ? (stats ? (KernelT)k_ao_persistent<true, true> : (KernelT)k_ao_persistent<false, true>)
+                                  : (stats ? (KernelT)k_ao_persistent<true, false> : (KernelT)k_ao_persistent<false, false>);
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kAoBlock, 0));
+    if (per_sm < 1) per_sm = 1;
+    const uint64_t resident_threads = (uint64_t)per_sm * ctx->sm_count * kAoBlock;
+    uint32_t n_chunks = 1;
+    while (n * n_chunks < 8 * resident_threads && n_chunks * 2 <= q2) n_chunks *= 2;
+    unsigned grid = (unsigned)(per_sm * ctx->sm_count);
+    const uint64_t items = n * n_chunks;
+    if ((uint64_t)grid * kAoBlock > items) grid = (unsigned)((items + kAoBlock - 1) / kAoBlock);
+    if (n_chunks > 1) CK(cudaMemsetAsync(ctx->d_hits.p + begin, 0, n * sizeof(uint32_t), st));
+    CK(cudaMemsetAsync(ctx->d_counter.p, 0, sizeof(unsigned long long), st));
+    const uint32_t refill = ctx->params.refill_below > 0 ? (uint32_t)ctx->params.refill_below : 24u;
+    kern<<<grid, kAoBlock, 0, st>>>(bvh, S, (uint64_t)begin, (uint32_t)n, q, offset, maxdist, n_chunks, refill, ctx->d_hits.p + begin,
+                                    ctx->d_counter.p, ctx->d_stats.p);
+    CKL();
+    launches++;
   }
   k_ao_finalize<<<grid_for(n, 256), 256, 0, st>>>(ctx->d_hits.p + begin, n, (float)(q * q), ctx->d_ao.p + begin);
   CKL();
+  launches++;
+  ctx->timings.kernel_launches = launches;
   CK(cudaEventRecord(ctx->ev1, st));
   if (host_ao) CK(cudaMemcpyAsync(host_ao, ctx->d_ao.p + begin, n * sizeof(float), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
