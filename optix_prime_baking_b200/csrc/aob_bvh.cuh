@@ -417,6 +417,30 @@ struct TraceCounters {
   uint32_t nodes, tris, insts;
 };
 
+// Any-hit over one leaf primitive group (bits of `mask` index triangles from `base`).
+template <int KZ>
+AOB_D bool test_tri_group_k(const F4* tris, uint32_t base, uint32_t mask, V3 org, const Shear& sh, float tmin, float tmax,
+                            uint32_t* tested) {
+  do {
+    const int b = ffs32(mask) - 1;
+    mask &= mask - 1u;
+    const uint64_t prim = (uint64_t)base + (uint32_t)b;
+    const F4 a = ld_f4(tris + 3 * prim), bb = ld_f4(tris + 3 * prim + 1), c = ld_f4(tris + 3 * prim + 2);
+    (*tested)++;
+    if (woop_hit_k<KZ>(org, sh, tmin, tmax, v3(a.x, a.y, a.z), v3(bb.x, bb.y, bb.z), v3(c.x, c.y, c.z))) return true;
+  } while (mask);
+  return false;
+}
+// The Woop shear constants are only needed by rays that reach a triangle: computed here, lazily.
+AOB_D bool test_tri_group(const F4* tris, uint32_t base, uint32_t mask, V3 org, V3 dir, float tmin, float tmax, uint32_t* tested) {
+  const Shear sh = make_shear(dir);
+  switch (sh.kz) {
+    case 0: return test_tri_group_k<0>(tris, base, mask, org, sh, tmin, tmax, tested);
+    case 1: return test_tri_group_k<1>(tris, base, mask, org, sh, tmin, tmax, tested);
+    default: return test_tri_group_k<2>(tris, base, mask, org, sh, tmin, tmax, tested);
+  }
+}
+
 // Any-hit traversal of one ray with a caller-provided stack of kStackSize entries.
 template <bool STATS>
 AOB_D bool trace_any_hit(const BvhView& bvh, V3 org, V3 dir, float tmin, float tmax, U2* stack, TraceCounters* cnt) {
@@ -444,19 +468,18 @@ AOB_D bool trace_any_hit(const BvhView& bvh, V3 org, V3 dir, float tmin, float t
       T = G;
       G.x = 0; G.y = 0;
     }
-    // the Woop shear constants are only needed by rays that reach a triangle: computed lazily,
-    // per primitive group
-    Shear sh;
-    if (T.y && in_blas) sh = make_shear(r.dir);
+    if (T.y && in_blas) {
+      uint32_t tested = 0;
+      const bool hit = test_tri_group(bvh.tris, T.x, T.y, r.org, r.dir, r.tmin, r.tmax, &tested);
+      if (STATS) cnt->tris += tested;
+      if (hit) return true;
+      T.y = 0;
+    }
     while (T.y) {
       const int b = ffs32(T.y) - 1;
       T.y &= T.y - 1u;
       const uint32_t prim = T.x + (uint32_t)b;
-      if (in_blas) {
-        const F4 a = ld_f4(bvh.tris + 3ull * prim), bb = ld_f4(bvh.tris + 3ull * prim + 1), c = ld_f4(bvh.tris + 3ull * prim + 2);
-        if (STATS) cnt->tris++;
-        if (woop_hit(r.org, sh, r.tmin, r.tmax, v3(a.x, a.y, a.z), v3(bb.x, bb.y, bb.z), v3(c.x, c.y, c.z))) return true;
-      } else {
+      {
         // instance leaf: save the TLAS continuation, switch to object space
         if (T.y) stack[sp++] = T;
         if (G.y & 0xff000000u) stack[sp++] = G;

@@ -400,8 +400,9 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
   };
 
   // per-lane item state
-  bool have_item = false, ray_active = false;
+  bool have_item = false, ray_active = false, exhausted = false;
   uint32_t rel = 0, pass = 0, pass_end = 0, nh = 0;
+  uint32_t supply_next = 0, supply_left = 0, supply_chunk = 0;  // warp-uniform
   V3 org = v3(0, 0, 0), nrm = v3(0, 0, 0), fnrm = v3(0, 0, 0);
   Onb onb;
   onb.t = onb.b = v3(0, 0, 0);
@@ -425,21 +426,31 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
       else hits[rel] = nh;
       have_item = false;
     }
-    if (!__any_sync(0xffffffffu, have_item)) {
-      // the whole warp is done with its block: fetch the next (block, chunk) item.  Blocks of
-      // consecutive samples keep the warp's rays spatially coherent (samples are emitted in
-      // triangle order), chunk-major numbering keeps concurrent warps on neighbouring blocks.
-      unsigned long long w = 0;
-      if (lane == 0) w = atomicAdd(counter, 1ull);
-      w = __shfl_sync(0xffffffffu, w, 0);
-      if (w >= total_items) break;
-      const uint32_t chunk = (uint32_t)(w / n_blocks);
-      const unsigned long long blk = w - (unsigned long long)chunk * n_blocks;
-      const unsigned long long rr = blk * 32ull + lane;
-      if (rr < n) {
-        rel = (uint32_t)rr;
-        pass = (uint32_t)(((uint64_t)chunk * q2) / n_chunks);
-        pass_end = (uint32_t)(((uint64_t)(chunk + 1) * q2) / n_chunks);
+    // Lanes that finished their item take the next sample of the warp's *supply block*: a block
+    // of 32 consecutive samples (x one strata chunk) fetched with one atomicAdd by the warp.
+    // Consecutive samples sit on the same few triangles (samples are emitted in triangle
+    // order), so whatever the lanes' progress the warp's rays stay spatially coherent, and no
+    // lane waits for the slowest sample of a block.
+    bool need = !have_item && !exhausted;
+    while (true) {
+      const uint32_t need_mask = __ballot_sync(0xffffffffu, need);
+      if (need_mask == 0u) break;
+      if (supply_left == 0u) {
+        unsigned long long w = 0;
+        if (lane == 0) w = atomicAdd(counter, 1ull);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= total_items) { exhausted = true; break; }
+        supply_chunk = (uint32_t)(w / n_blocks);  // chunk-major: concurrent warps work on neighbouring blocks
+        const unsigned long long blk = w - (unsigned long long)supply_chunk * n_blocks;
+        supply_next = (uint32_t)(blk * 32ull);
+        supply_left = (uint32_t)min(32ull, (unsigned long long)n - blk * 32ull);
+      }
+      const uint32_t my = (uint32_t)__popc(need_mask & lt_mask);
+      const uint32_t take = min((uint32_t)__popc(need_mask), supply_left);
+      if (need && my < take) {
+        rel = supply_next + my;
+        pass = (uint32_t)(((uint64_t)supply_chunk * q2) / n_chunks);
+        pass_end = (uint32_t)(((uint64_t)(supply_chunk + 1) * q2) / n_chunks);
         const uint64_t g = begin + rel;
         const V3 p = v3(S.pos[3 * g], S.pos[3 * g + 1], S.pos[3 * g + 2]);
         nrm = v3(S.nrm[3 * g], S.nrm[3 * g + 1], S.nrm[3 * g + 2]);
@@ -448,7 +459,10 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
         org = ao_ray_origin(p, nrm, offset);
         nh = 0;
         have_item = true;
+        need = false;
       }
+      supply_next += take;
+      supply_left -= take;
     }
     if (!ray_active && have_item && pass < pass_end) {
       wdir = ao_ray_dir((uint32_t)(begin + rel), pass, q, nrm, fnrm, onb);
@@ -461,7 +475,10 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
       sp = 0;
       ray_active = true;
     }
-    if (!__any_sync(0xffffffffu, ray_active)) continue;  // block finished (or empty): commit + fetch next
+    if (!__any_sync(0xffffffffu, ray_active)) {
+      if (exhausted && !__any_sync(0xffffffffu, have_item)) break;  // nothing in flight and nothing left
+      continue;
+    }
 
     // ------------------------------ traverse ------------------------------
     while (true) {
@@ -486,15 +503,9 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
         bool hit = false;
         if (T.y) {
           if (in_blas) {
-            const Shear sh = make_shear(r.dir);
-            do {
-              const int b = __ffs((int)T.y) - 1;
-              T.y &= T.y - 1u;
-              const uint64_t prim = (uint64_t)T.x + (uint32_t)b;
-              const F4 a = ld_f4(bvh.tris + 3 * prim), bb = ld_f4(bvh.tris + 3 * prim + 1), c = ld_f4(bvh.tris + 3 * prim + 2);
-              if (STATS) c_tris++;
-              hit = woop_hit(r.org, sh, 0.0f, maxdist, v3(a.x, a.y, a.z), v3(bb.x, bb.y, bb.z), v3(c.x, c.y, c.z));
-            } while (T.y && !hit);
+            uint32_t tested = 0;
+            hit = test_tri_group(bvh.tris, T.x, T.y, r.org, r.dir, 0.0f, maxdist, &tested);
+            if (STATS) c_tris += tested;
           } else if (TWO_LEVEL) {
             // first instance of the group: save the TLAS continuation, switch to object space
             const int b = __ffs((int)T.y) - 1;
@@ -538,7 +549,7 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
       if (act == 0u) break;
       if ((uint32_t)__popc(act) < refill_below) {
         // leave only if some idle lane can actually take a new ray
-        const bool can = !ray_active && have_item && pass < pass_end;
+        const bool can = !ray_active && ((have_item && pass < pass_end) || !exhausted);
         if (__any_sync(0xffffffffu, can)) break;
       }
     }

@@ -197,29 +197,39 @@ AOB_HD V3 ao_ray_origin(V3 p, V3 n, float offset) {
 }
 
 // ---- watertight ray/triangle (Woop, Benthin, Wald 2013), any-hit with (tmin, tmax) --------
+// kz = dominant axis of the direction, (kx, ky) the next two cyclically; Sz = 1/d[kz] (IEEE),
+// Sx = d[kx]*Sz, Sy = d[ky]*Sz.  The paper's kx<->ky swap for d[kz] < 0 only flips the sign of
+// U, V, W, det and T *exactly* (fl(a-b) = -fl(b-a)), which neither the same-sign test nor the
+// range test can see, so it is omitted here (the oracle keeps it; decisions are identical).
+// The test is specialised on kz at compile time: no runtime component selects, everything on
+// the FMA pipe, and the three copies cost nothing extra because only a lane or two of a warp
+// are in a triangle test at any time.
 struct Shear {
-  int kx, ky, kz;
+  int kz;
   float Sx, Sy, Sz;
 };
 AOB_HD Shear make_shear(V3 d) {
   Shear s;
   float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
   s.kz = (ax > ay) ? ((ax > az) ? 0 : 2) : ((ay > az) ? 1 : 2);
-  s.kx = s.kz + 1; if (s.kx == 3) s.kx = 0;
-  s.ky = s.kx + 1; if (s.ky == 3) s.ky = 0;
-  float dz = comp(d, s.kz);
-  if (dz < 0.0f) { int t = s.kx; s.kx = s.ky; s.ky = t; }
-  s.Sx = ex::div(comp(d, s.kx), dz);
-  s.Sy = ex::div(comp(d, s.ky), dz);
+  const float dz = s.kz == 0 ? d.x : (s.kz == 1 ? d.y : d.z);
+  const float dx = s.kz == 0 ? d.y : (s.kz == 1 ? d.z : d.x);
+  const float dy = s.kz == 0 ? d.z : (s.kz == 1 ? d.x : d.y);
   s.Sz = ex::div(1.0f, dz);
+  s.Sx = ex::mul(dx, s.Sz);
+  s.Sy = ex::mul(dy, s.Sz);
   return s;
 }
-AOB_HD bool woop_hit(V3 org, const Shear& s, float tmin, float tmax, V3 p0, V3 p1, V3 p2) {
-  V3 A = sub(p0, org), B = sub(p1, org), C = sub(p2, org);
-  float Akz = comp(A, s.kz), Bkz = comp(B, s.kz), Ckz = comp(C, s.kz);
-  float Ax = ex::sub(comp(A, s.kx), ex::mul(s.Sx, Akz)), Ay = ex::sub(comp(A, s.ky), ex::mul(s.Sy, Akz));
-  float Bx = ex::sub(comp(B, s.kx), ex::mul(s.Sx, Bkz)), By = ex::sub(comp(B, s.ky), ex::mul(s.Sy, Bkz));
-  float Cx = ex::sub(comp(C, s.kx), ex::mul(s.Sx, Ckz)), Cy = ex::sub(comp(C, s.ky), ex::mul(s.Sy, Ckz));
+template <int KZ>
+AOB_HD bool woop_hit_k(V3 org, const Shear& s, float tmin, float tmax, V3 p0, V3 p1, V3 p2) {
+  const V3 A = sub(p0, org), B = sub(p1, org), C = sub(p2, org);
+  // (kx, ky, kz) = (KZ+1, KZ+2, KZ) mod 3
+  const float Akz = KZ == 0 ? A.x : (KZ == 1 ? A.y : A.z), Akx = KZ == 0 ? A.y : (KZ == 1 ? A.z : A.x), Aky = KZ == 0 ? A.z : (KZ == 1 ? A.x : A.y);
+  const float Bkz = KZ == 0 ? B.x : (KZ == 1 ? B.y : B.z), Bkx = KZ == 0 ? B.y : (KZ == 1 ? B.z : B.x), Bky = KZ == 0 ? B.z : (KZ == 1 ? B.x : B.y);
+  const float Ckz = KZ == 0 ? C.x : (KZ == 1 ? C.y : C.z), Ckx = KZ == 0 ? C.y : (KZ == 1 ? C.z : C.x), Cky = KZ == 0 ? C.z : (KZ == 1 ? C.x : C.y);
+  const float Ax = ex::sub(Akx, ex::mul(s.Sx, Akz)), Ay = ex::sub(Aky, ex::mul(s.Sy, Akz));
+  const float Bx = ex::sub(Bkx, ex::mul(s.Sx, Bkz)), By = ex::sub(Bky, ex::mul(s.Sy, Bkz));
+  const float Cx = ex::sub(Ckx, ex::mul(s.Sx, Ckz)), Cy = ex::sub(Cky, ex::mul(s.Sy, Ckz));
   float U = ex::sub(ex::mul(Cx, By), ex::mul(Cy, Bx));
   float V = ex::sub(ex::mul(Ax, Cy), ex::mul(Ay, Cx));
   float W = ex::sub(ex::mul(Bx, Ay), ex::mul(By, Ax));
@@ -229,12 +239,21 @@ AOB_HD bool woop_hit(V3 org, const Shear& s, float tmin, float tmax, V3 p0, V3 p
     W = (float)ex::dsub(ex::dmul((double)Bx, (double)Ay), ex::dmul((double)By, (double)Ax));
   }
   if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
-  float det = ex::add(ex::add(U, V), W);
+  const float det = ex::add(ex::add(U, V), W);
   if (det == 0.0f) return false;
-  float Az = ex::mul(s.Sz, Akz), Bz = ex::mul(s.Sz, Bkz), Cz = ex::mul(s.Sz, Ckz);
-  float T = ex::add(ex::add(ex::mul(U, Az), ex::mul(V, Bz)), ex::mul(W, Cz));
-  float t = ex::div(T, det);
-  return (t > tmin) && (t < tmax);
+  const float Az = ex::mul(s.Sz, Akz), Bz = ex::mul(s.Sz, Bkz), Cz = ex::mul(s.Sz, Ckz);
+  const float T = ex::add(ex::add(ex::mul(U, Az), ex::mul(V, Bz)), ex::mul(W, Cz));
+  // division-free range test: T*sign(det) against t*|det|
+  const float ad = fabsf(det);
+  const float Ts = det < 0.0f ? -T : T;
+  return (Ts > ex::mul(tmin, ad)) && (Ts < ex::mul(tmax, ad));
+}
+AOB_HD bool woop_hit(V3 org, const Shear& s, float tmin, float tmax, V3 p0, V3 p1, V3 p2) {
+  switch (s.kz) {
+    case 0: return woop_hit_k<0>(org, s, tmin, tmax, p0, p1, p2);
+    case 1: return woop_hit_k<1>(org, s, tmin, tmax, p0, p1, p2);
+    default: return woop_hit_k<2>(org, s, tmin, tmax, p0, p1, p2);
+  }
 }
 
 }  // namespace aob

@@ -279,9 +279,9 @@ inline RayShear make_shear(V3 d) {
   s.kx = s.kz + 1; if (s.kx == 3) s.kx = 0;
   s.ky = s.kx + 1; if (s.ky == 3) s.ky = 0;
   if (comp(d, s.kz) < 0.0f) std::swap(s.kx, s.ky);
-  s.Sx = comp(d, s.kx) / comp(d, s.kz);
-  s.Sy = comp(d, s.ky) / comp(d, s.kz);
   s.Sz = 1.0f / comp(d, s.kz);
+  s.Sx = comp(d, s.kx) * s.Sz;
+  s.Sy = comp(d, s.ky) * s.Sz;
   return s;
 }
 // Returns true on hit; *margin (optional) = min(|U|,|V|,|W|)/|det| (distance to the nearest
@@ -306,13 +306,12 @@ inline bool woop_hit(const Ray& r, const RayShear& s, V3 p0, V3 p1, V3 p2, float
   if (det == 0.0f) return false;
   float Az = s.Sz * comp(A, s.kz), Bz = s.Sz * comp(B, s.kz), Cz = s.Sz * comp(C, s.kz);
   float T = (U * Az + V * Bz) + W * Cz;
-  float t = T / det;
-  if (t_out) *t_out = t;
-  if (margin) {
-    float ad = std::fabs(det);
-    *margin = std::min(std::fabs(U), std::min(std::fabs(V), std::fabs(W))) / ad;
-  }
-  return (t > r.tmin) && (t < r.tmax);
+  // range test without a division (Woop et al. §3.2): compare T*sign(det) with t*|det|
+  const float ad = std::fabs(det);
+  const float Ts = det < 0.0f ? -T : T;
+  if (t_out) *t_out = T / det;
+  if (margin) *margin = std::min(std::fabs(U), std::min(std::fabs(V), std::fabs(W))) / ad;
+  return (Ts > r.tmin * ad) && (Ts < r.tmax * ad);
 }
 
 struct Box {

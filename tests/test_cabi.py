@@ -1,0 +1,71 @@
+"""The C-ABI boundary: libaobake.so loads and exports every symbol include/aobake.h declares;
+the C++ bake:: shim compiles and links with plain g++ (CPU), and runs on the GPU."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "optix_prime_baking_b200", "libaobake.so")
+GXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "aobake.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(aobake_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib_path():
+    from optix_prime_baking_b200 import build
+    return build.build()
+
+
+def test_library_exports_every_declared_symbol(lib_path):
+    names = declared_symbols()
+    assert len(names) >= 20
+    lib = ctypes.CDLL(lib_path)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in aobake.h but not exported"
+    from optix_prime_baking_b200 import api
+    assert sorted(api.EXPORTS) == names
+
+
+def test_pure_host_entry_points(lib_path):
+    """Entry points that need no device: defaults, ground plane, error text, create without a GPU."""
+    from optix_prime_baking_b200 import api
+    p = api.default_params()
+    assert p.device == 0 and p.cg_max_iterations > 0 and p.cg_tolerance > 0
+    v, t = api.make_ground_plane([-1, -1, -1], [1, 1, 1], 1, 100.0, 0.03)
+    assert v.shape == (4, 3) and abs(v[0, 1] - (-1 - 0.06)) < 1e-6 and abs(abs(v[:, 0]).max() - 100.0) < 1e-4
+    with pytest.raises(api.AoBakeError):
+        api.make_ground_plane([0, 0, 0], [1, 1, 1], 9)
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(api.AoBakeError) as ei:       # loud failure, never a CPU fallback
+            api.Baker()
+        assert "no CUDA device" in str(ei.value) or ei.value.code in (2, 5)
+
+
+def _compile_cpp(tmp_path):
+    exe = str(tmp_path / "test_bake_api")
+    cmd = [GXX, "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "test_bake_api.cpp"),
+           "-o", exe, "-L", os.path.dirname(LIB), "-laobake", f"-Wl,-rpath,{os.path.dirname(LIB)}"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    return exe
+
+
+def test_cpp_shim_compiles_and_links(lib_path, tmp_path):
+    _compile_cpp(tmp_path)
+
+
+@pytest.mark.gpu
+def test_cpp_shim_runs(lib_path, tmp_path):
+    exe = _compile_cpp(tmp_path)
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "bake_api ok" in res.stdout
