@@ -225,7 +225,8 @@ def main():
     q = int(np.float32(np.sqrt(np.float32(rays))) + np.float32(0.5))
 
     bk = api.Baker(device=local_rank, trace_kernel=args.trace_kernel)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # the launch stream: kernels and timing events share it
+    torch.cuda.set_stream(stream)
     bk.set_stream(stream.cuda_stream)
     bk.set_scene(scene, blockers)
     base_total, _ = bk.distribute_samples(min_per, requested)
@@ -260,6 +261,7 @@ def main():
         step()
         b.record(stream)
         kernel_ms.append(bk.timings().trace_ms)
+        launches_per_step = bk.timings().kernel_launches
     barrier()
     clocks = sampler.stop()
     ms = sum(a.elapsed_time(b) for a, b in ev)
@@ -298,13 +300,22 @@ def main():
         barrier()
         t0 = time.perf_counter()
         with api.Baker(device=local_rank, trace_kernel=args.trace_kernel) as b2:
+            t1 = time.perf_counter()
             b2.set_scene(scene, blockers)
+            t2 = time.perf_counter()
             b2.set_samples(pin)
+            t3 = time.perf_counter()
             b2.compute_ao(rays, off, maxd, download=True, out=ao_host)
+            t4 = time.perf_counter()
+            tm2 = b2.timings()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if s >= 1:
             e2e_times.append(dt)
+            e2e_break = {"create_ms": (t1 - t0) * 1e3, "set_scene_ms": (t2 - t1) * 1e3, "scene_upload_ms": tm2.upload_ms,
+                         "bvh_build_ms": tm2.bvh_build_ms, "set_samples_ms": (t3 - t2) * 1e3,
+                         "compute_ao_plus_download_ms": (t4 - t3) * 1e3, "trace_kernel_ms": tm2.trace_ms,
+                         "destroy_ms": (time.perf_counter() - t4) * 1e3}
     te = torch.tensor([float(np.mean(e2e_times))], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -347,8 +358,8 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "what": "computeAO(scene, blockers, samples) with pinned host buffers: scene upload + BVH build + "
-                            "sample upload + trace + AO download", "seconds_per_step": float(te.item())},
-            "gpu_launches": 2 * args.steps,
+                            "sample upload + trace + AO download", "seconds_per_step": float(te.item()), "breakdown_rank0": e2e_break},
+            "gpu_launches": int(launches_per_step) * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "k_ao (fused raygen+traverse+accumulate)",
                          "kernel_ms": kms, "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray,

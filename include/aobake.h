@@ -112,9 +112,9 @@ typedef struct AoBakeParams {
   int32_t instancing_mode;        /* AoInstancingMode */
   int32_t cg_max_iterations;      /* least-squares filter */
   float   cg_tolerance;           /* relative residual */
-  int32_t trace_kernel;           /* 0 = default (persistent, refilling); 1 = simple one-ray-per-thread */
+  int32_t trace_kernel;           /* 0 = auto (persistent refilling kernel; simple kernel below 32 M rays); 1 = simple; 2 = persistent */
   int32_t collect_stats;          /* 1: count node visits / triangle tests in aobake_compute_ao */
-  int32_t refill_below;           /* persistent kernel: refill a warp when fewer lanes are traversing (0 = default 24) */
+  int32_t refill_below;           /* persistent kernel: refill a warp when fewer lanes are traversing (0 = default 28) */
   int32_t reserved[7];
 } AoBakeParams;
 

@@ -101,6 +101,38 @@ __global__ void k_bounds(const F4* __restrict__ plo, const F4* __restrict__ phi,
     }
   }
 }
+// world-space box of one instance: every vertex of its mesh through the instance transform
+// (tighter than transforming the 8 corners of the object-space box, which for a rotated mesh can
+// inflate the TLAS leaf several-fold).  b6 must be initialised with k_init_bounds.
+__global__ void k_instance_bounds(const float* __restrict__ verts, uint32_t nV, Xf12 xf, int* b6) {
+  float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nV; i += gridDim.x * blockDim.x) {
+    const V3 w = xf_point(xf.m, v3(verts[3ull * i], verts[3ull * i + 1], verts[3ull * i + 2]));
+    lo[0] = fminf(lo[0], w.x); lo[1] = fminf(lo[1], w.y); lo[2] = fminf(lo[2], w.z);
+    hi[0] = fmaxf(hi[0], w.x); hi[1] = fmaxf(hi[1], w.y); hi[2] = fmaxf(hi[2], w.z);
+  }
+#pragma unroll
+  for (int k = 0; k < 3; k++)
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+      hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+    }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      atomicMin(&b6[k], float_to_ordered(lo[k]));
+      atomicMax(&b6[3 + k], float_to_ordered(hi[k]));
+    }
+  }
+}
+__global__ void k_decode_bounds_n(const int* f6, float* out6, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out6[i] = ordered_to_float(f6[i]);
+}
+__global__ void k_init_bounds_n(int* b6, uint32_t n_boxes) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 6 * n_boxes) b6[i] = (i % 6 < 3) ? 0x7fffffff : (int)0x80000000;
+}
 __global__ void k_decode_bounds(const int* f6, float* out6) {
   if (threadIdx.x < 6) out6[threadIdx.x] = ordered_to_float(f6[threadIdx.x]);
 }
@@ -400,6 +432,8 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
   };
 
   // per-lane item state
+  __shared__ float s_la[3][kAoBlock];  // queued (lookahead) ray direction per thread
+  bool la_valid = false;
   bool have_item = false, ray_active = false, exhausted = false;
   uint32_t rel = 0, pass = 0, pass_end = 0, nh = 0;
   uint32_t supply_next = 0, supply_left = 0, supply_chunk = 0;  // warp-uniform
@@ -418,10 +452,21 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
   uint32_t c_nodes = 0, c_tris = 0, c_insts = 0;
   const unsigned long long n_blocks = ((unsigned long long)n + 31ull) / 32ull;
   const unsigned long long total_items = n_blocks * n_chunks;  // item = (block of 32 samples, strata chunk)
+  auto start_queued = [&]() {
+    wdir = v3(s_la[0][threadIdx.x], s_la[1][threadIdx.x], s_la[2][threadIdx.x]);
+    la_valid = false;
+    r.org = org; r.dir = wdir;
+    r.idir = v3(safe_rcp(wdir.x), safe_rcp(wdir.y), safe_rcp(wdir.z));
+    in_blas = !TWO_LEVEL;
+    G.x = bvh.root;
+    G.y = (1u << 24) | 1u;
+    sp = 0;
+    ray_active = true;
+  };
 
   while (true) {
     // ------------------------------ refill ------------------------------
-    if (!ray_active && have_item && pass == pass_end) {
+    if (!ray_active && !la_valid && have_item && pass == pass_end) {
       if (n_chunks > 1) atomicAdd(&hits[rel], nh);
       else hits[rel] = nh;
       have_item = false;
@@ -464,17 +509,17 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
       supply_next += take;
       supply_left -= take;
     }
-    if (!ray_active && have_item && pass < pass_end) {
-      wdir = ao_ray_dir((uint32_t)(begin + rel), pass, q, nrm, fnrm, onb);
+    // One-deep lookahead: at a refill *every* lane without a queued ray generates its next one
+    // (idle lanes and lanes still traversing alike), so ray generation runs with most of the
+    // warp converged instead of only the few idle lanes; a lane whose ray ends inside the
+    // traversal loop starts its queued ray at once, without a refill.
+    if (have_item && !la_valid && pass < pass_end) {
+      const V3 d = ao_ray_dir((uint32_t)(begin + rel), pass, q, nrm, fnrm, onb);
       pass++;
-      r.org = org; r.dir = wdir;
-      r.idir = v3(safe_rcp(wdir.x), safe_rcp(wdir.y), safe_rcp(wdir.z));
-      in_blas = !TWO_LEVEL;
-      G.x = bvh.root;
-      G.y = (1u << 24) | 1u;
-      sp = 0;
-      ray_active = true;
+      s_la[0][threadIdx.x] = d.x; s_la[1][threadIdx.x] = d.y; s_la[2][threadIdx.x] = d.z;
+      la_valid = true;
     }
+    if (!ray_active && la_valid) start_queued();
     if (!__any_sync(0xffffffffu, ray_active)) {
       if (exhausted && !__any_sync(0xffffffffu, have_item)) break;  // nothing in flight and nothing left
       continue;
@@ -531,9 +576,14 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
         if (hit) {
           nh++;
           ray_active = false;
+          if (la_valid) start_queued();
         } else if ((G.y & 0xff000000u) == 0u) {
           while (true) {
-            if (sp == 0) { ray_active = false; break; }
+            if (sp == 0) {
+              ray_active = false;
+              if (la_valid) start_queued();
+              break;
+            }
             G = pop(sp);
             if (TWO_LEVEL && G.x == kSentinel && G.y == 0u) {
               r.org = org; r.dir = wdir;
@@ -549,7 +599,7 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
       if (act == 0u) break;
       if ((uint32_t)__popc(act) < refill_below) {
         // leave only if some idle lane can actually take a new ray
-        const bool can = !ray_active && ((have_item && pass < pass_end) || !exhausted);
+        const bool can = !ray_active && ((have_item && pass < pass_end) || !exhausted);  // (a queued ray would already have started)
         if (__any_sync(0xffffffffu, can)) break;
       }
     }

@@ -23,6 +23,10 @@ using namespace aob;
 namespace {
 
 thread_local std::string g_create_error;
+// Stream-ordered allocations (cudaMallocAsync) on the stream of the API call in progress: the
+// BVH build and the filters allocate dozens of scratch buffers, and the driver's pool makes
+// those microseconds instead of the milliseconds of cudaMalloc/cudaFree.
+thread_local cudaStream_t g_alloc_stream = nullptr;
 
 template <typename T>
 struct DBuf {
@@ -41,10 +45,10 @@ struct DBuf {
     release();
     n = count;
     if (count == 0) return cudaSuccess;
-    return cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T));
+    return cudaMallocAsync(reinterpret_cast<void**>(&p), count * sizeof(T), g_alloc_stream);
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) cudaFreeAsync(p, g_alloc_stream);
     p = nullptr;
     n = 0;
   }
@@ -330,7 +334,7 @@ BvhView bvh_view(const AoBake* ctx) {
 struct ScopedTimer {
   AoBake* c;
   double t0;
-  explicit ScopedTimer(AoBake* ctx) : c(ctx), t0(now_ms()) {}
+  explicit ScopedTimer(AoBake* ctx) : c(ctx), t0(now_ms()) { g_alloc_stream = ctx->stream; }
   ~ScopedTimer() { c->timings.host_total_ms = (float)(now_ms() - t0); }
 };
 
@@ -380,7 +384,14 @@ int aobake_create(const AoBakeParams* params, AoBake** out) {
   ctx->params = p;
   ctx->device = p.device;
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, p.device);
-  if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+  {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, p.device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;  // keep freed scratch in the pool between calls
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
+  if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess || ((g_alloc_stream = ctx->own_stream), false) ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
       ctx->d_stats.alloc(4) != cudaSuccess || ctx->d_counter.alloc(1) != cudaSuccess) {
     g_create_error = std::string("context setup: ") + cudaGetErrorString(cudaGetLastError());
@@ -396,16 +407,21 @@ void aobake_destroy(AoBake* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  g_alloc_stream = ctx->own_stream;
+  cudaStream_t own = ctx->own_stream;
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
-  delete ctx;
+  delete ctx;  // frees every buffer stream-ordered on `own`
+  if (own) { cudaStreamSynchronize(own); cudaStreamDestroy(own); }
+  g_alloc_stream = nullptr;
 }
 
 int aobake_set_stream(AoBake* ctx, void* s) {
   if (!ctx) return AOBAKE_ERR_INVALID_ARGUMENT;
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->stream = s ? reinterpret_cast<cudaStream_t>(s) : ctx->own_stream;
+  CK(cudaStreamSynchronize(ctx->stream));
+  g_alloc_stream = ctx->stream;
   return AOBAKE_OK;
 }
 int aobake_synchronize(AoBake* ctx) {
@@ -538,29 +554,45 @@ int aobake_set_scene(AoBake* ctx, const AoScene* scene, const AoScene* blockers)
       node_off += segs[mi].node_count;
       prim_off += n;
     }
-    // TLAS over instance world boxes (8 transformed corners of the BLAS box, padded)
+    // TLAS over instance world boxes: every mesh vertex through the instance transform (exact
+    // fp32 formula), padded by a few ulp against the rounding of the inverse transform.
     const uint32_t nI = (uint32_t)all.size();
     std::vector<F4> hlo(std::max(nI, 1u)), hhi(std::max(nI, 1u));
     std::vector<uint32_t> inst_blas(nI);
-    for (uint32_t i = 0; i < nI; i++) {
-      const bool is_blocker = i >= ctx->insts.size();
-      const uint32_t mi = all[i].inst->mesh + (is_blocker ? (uint32_t)ctx->meshes.size() : 0u);
-      inst_blas[i] = mi;
-      const float* b = segs[mi].box;
-      F4 lo, hi;
-      lo.x = lo.y = lo.z = 3.0e38f; hi.x = hi.y = hi.z = -3.0e38f; lo.w = hi.w = 0.f;
-      if (ml[mi]->nT == 0) { lo.x = lo.y = lo.z = 0.f; hi = lo; }
-      else {
-        for (int c = 0; c < 8; c++) {
-          V3 p = xf_point(all[i].inst->xf, v3((c & 1) ? b[3] : b[0], (c & 2) ? b[4] : b[1], (c & 4) ? b[5] : b[2]));
-          lo.x = fminf(lo.x, p.x); lo.y = fminf(lo.y, p.y); lo.z = fminf(lo.z, p.z);
-          hi.x = fmaxf(hi.x, p.x); hi.y = fmaxf(hi.y, p.y); hi.z = fmaxf(hi.z, p.z);
-        }
-        const float px = 3.8e-6f * fmaxf(fabsf(lo.x), fabsf(hi.x)), py = 3.8e-6f * fmaxf(fabsf(lo.y), fabsf(hi.y)),
-                    pz = 3.8e-6f * fmaxf(fabsf(lo.z), fabsf(hi.z));
-        lo.x -= px; lo.y -= py; lo.z -= pz; hi.x += px; hi.y += py; hi.z += pz;
+    {
+      DBuf<int> d_ib;
+      DBuf<float> d_fb;
+      CK(d_ib.alloc(6ull * std::max(nI, 1u)));
+      CK(d_fb.alloc(6ull * std::max(nI, 1u)));
+      if (nI) k_init_bounds_n<<<grid_for(6ull * nI, 256), 256, 0, st>>>(d_ib.p, nI);
+      for (uint32_t i = 0; i < nI; i++) {
+        const DeviceMesh* m = all[i].mesh;
+        if (!m->nV) continue;
+        Xf12 xf;
+        memcpy(xf.m, all[i].inst->xf, sizeof(xf.m));
+        k_instance_bounds<<<std::min<unsigned>(grid_for(m->nV, 256), 64u), 256, 0, st>>>(m->verts.p, (uint32_t)m->nV, xf, d_ib.p + 6ull * i);
       }
-      hlo[i] = lo; hhi[i] = hi;
+      if (nI) k_decode_bounds_n<<<grid_for(6ull * nI, 256), 256, 0, st>>>(d_ib.p, d_fb.p, 6 * nI);
+      CKL();
+      std::vector<float> hb(6ull * std::max(nI, 1u));
+      if (nI) CK(cudaMemcpyAsync(hb.data(), d_fb.p, 6ull * nI * sizeof(float), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      for (uint32_t i = 0; i < nI; i++) {
+        const bool is_blocker = i >= ctx->insts.size();
+        const uint32_t mi = all[i].inst->mesh + (is_blocker ? (uint32_t)ctx->meshes.size() : 0u);
+        inst_blas[i] = mi;
+        F4 lo, hi;
+        lo.w = hi.w = 0.f;
+        if (ml[mi]->nT == 0 || ml[mi]->nV == 0) { lo.x = lo.y = lo.z = 0.f; hi = lo; }
+        else {
+          const float* b = &hb[6ull * i];
+          lo.x = b[0]; lo.y = b[1]; lo.z = b[2]; hi.x = b[3]; hi.y = b[4]; hi.z = b[5];
+          const float px = 3.8e-6f * fmaxf(fabsf(lo.x), fabsf(hi.x)), py = 3.8e-6f * fmaxf(fabsf(lo.y), fabsf(hi.y)),
+                      pz = 3.8e-6f * fmaxf(fabsf(lo.z), fabsf(hi.z));
+          lo.x -= px; lo.y -= py; lo.z -= pz; hi.x += px; hi.y += py; hi.z += pz;
+        }
+        hlo[i] = lo; hhi[i] = hi;
+      }
     }
     DBuf<F4> plo, phi;
     DBuf<uint32_t> leaf_insts;
@@ -572,7 +604,8 @@ int aobake_set_scene(AoBake* ctx, const AoScene* scene, const AoScene* blockers)
     Segment tl;
     if ((rc = build_segment(ctx, plo.p, phi.p, nI, 1, node_off, 0, nodes.p, leaf_insts.p, &tl))) return rc;
     std::vector<uint32_t> order(nI);
-    if (nI) CK(cudaMemcpy(order.data(), leaf_insts.p, nI * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (nI) CK(cudaMemcpyAsync(order.data(), leaf_insts.p, nI * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     std::vector<F4> recs(4ull * std::max(nI, 1u));
     for (uint32_t k = 0; k < nI; k++) {
       const HostInstance* I = all[order[k]].inst;
@@ -583,7 +616,8 @@ int aobake_set_scene(AoBake* ctx, const AoScene* scene, const AoScene* blockers)
       recs[4ull * k + 3] = f;
     }
     CK(ctx->d_insts.alloc(recs.size()));
-    CK(cudaMemcpy(ctx->d_insts.p, recs.data(), recs.size() * sizeof(F4), cudaMemcpyHostToDevice));
+    CK(cudaMemcpyAsync(ctx->d_insts.p, recs.data(), recs.size() * sizeof(F4), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
     const uint32_t total_nodes = node_off + tl.node_count;
     CK(ctx->d_nodes.alloc(total_nodes));
     CK(cudaMemcpyAsync(ctx->d_nodes.p, nodes.p, total_nodes * sizeof(Node8), cudaMemcpyDeviceToDevice, st));
@@ -648,7 +682,8 @@ int aobake_sample_instances(AoBake* ctx, const size_t* per_instance, size_t min_
   const uint32_t ni = (uint32_t)ctx->insts.size();
   uint64_t total = 0;
   std::vector<InstDesc> h(ni);
-  if (ni) CK(cudaMemcpy(h.data(), ctx->d_inst.p, ni * sizeof(InstDesc), cudaMemcpyDeviceToHost));
+  if (ni) CK(cudaMemcpyAsync(h.data(), ctx->d_inst.p, ni * sizeof(InstDesc), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
   for (uint32_t i = 0; i < ni; i++) {
     if (per_instance[i] < min_per_tri * h[i].num_tris)
       return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "instance %u: %llu samples < minimum %llu", i, (unsigned long long)per_instance[i],
@@ -758,7 +793,10 @@ int aobake_compute_ao_range(AoBake* ctx, size_t begin, size_t end, int rays_per_
   CK(cudaEventRecord(ctx->ev0, st));
   const uint32_t q2 = (uint32_t)(q * q);
   int launches = 0;
-  if (ctx->params.trace_kernel == 1) {
+  // trace_kernel: 0 = auto (persistent, except for launches too small to amortise its work
+  // distribution: < 32 M rays), 1 = simple, 2 = persistent
+  const bool use_simple = ctx->params.trace_kernel == 1 || (ctx->params.trace_kernel == 0 && n * (uint64_t)q2 < (32ull << 20));
+  if (use_simple) {
     // simple variant: enough (sample block, strata chunk) items to fill the machine
     const uint64_t n_blocks = (n + 31) / 32;
     const uint64_t want = (uint64_t)ctx->sm_count * 64ull * 4ull;
@@ -791,7 +829,7 @@ int aobake_compute_ao_range(AoBake* ctx, size_t begin, size_t end, int rays_per_
     if ((uint64_t)grid * kAoBlock > items) grid = (unsigned)((items + kAoBlock - 1) / kAoBlock);
     if (n_chunks > 1) CK(cudaMemsetAsync(ctx->d_hits.p + begin, 0, n * sizeof(uint32_t), st));
     CK(cudaMemsetAsync(ctx->d_counter.p, 0, sizeof(unsigned long long), st));
-    const uint32_t refill = ctx->params.refill_below > 0 ? (uint32_t)ctx->params.refill_below : 24u;
+    const uint32_t refill = ctx->params.refill_below > 0 ? (uint32_t)ctx->params.refill_below : 28u;
     kern<<<grid, kAoBlock, 0, st>>>(bvh, S, (uint64_t)begin, (uint32_t)n, q, offset, maxdist, n_chunks, refill, ctx->d_hits.p + begin,
                                     ctx->d_counter.p, ctx->d_stats.p);
     CKL();
@@ -807,7 +845,8 @@ int aobake_compute_ao_range(AoBake* ctx, size_t begin, size_t end, int rays_per_
   CK(cudaEventElapsedTime(&ctx->timings.trace_ms, ctx->ev0, ctx->ev1));
   if (stats) {
     unsigned long long hs[4];
-    CK(cudaMemcpy(hs, ctx->d_stats.p, sizeof(hs), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpyAsync(hs, ctx->d_stats.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     ctx->stats.node_visits = hs[0]; ctx->stats.triangle_tests = hs[1]; ctx->stats.instance_entries = hs[2];
     ctx->stats.rays = ctx->timings.rays_traced;
   }

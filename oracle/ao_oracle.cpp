@@ -642,11 +642,14 @@ void sample_instance(const OrScene& sc, uint64_t inst, uint64_t n_samples, uint6
 // ----------------------------------------------------------------------------------
 inline int sqrt_rays(int rays_per_sample) { return (int)(std::sqrt((float)rays_per_sample) + 0.5f); }
 
-inline Ray make_ray(const OrSamples& S, uint64_t g, int px, int py, int q, float offset, float maxdist) {
+// `g` indexes the sample arrays; `gid` is the global sample index that keys the RNG (they differ
+// only when a caller passes a subset of a larger sample set).
+inline Ray make_ray(const OrSamples& S, uint64_t g, int px, int py, int q, float offset, float maxdist, uint64_t gid = ~0ull) {
+  if (gid == ~0ull) gid = g;
   V3 p = load3(S.sample_positions + 3 * g), n = load3(S.sample_normals + 3 * g),
      fn = load3(S.sample_face_normals + 3 * g);
   const uint32_t pass = (uint32_t)(px * q + py);
-  uint32_t seed = tea(2, (pass << 16) | pass, (uint32_t)g);  // decision #10
+  uint32_t seed = tea(2, (pass << 16) | pass, (uint32_t)gid);  // decision #10
   // optix::Onb about the shading normal
   V3 b;
   if (std::fabs(n.x) > std::fabs(n.z)) b = v3(-n.y, n.x, 0.0f); else b = v3(0.0f, -n.z, n.y);
@@ -877,6 +880,20 @@ int ao_oracle_generate_rays(const OrSamples* S, uint64_t begin, uint64_t end, in
         o[4] = r.d.x; o[5] = r.d.y; o[6] = r.d.z; o[7] = r.tmax;
       }
   }
+  return 0;
+}
+
+// rays of local sample `k` generated with the RNG streams of global sample index `gid`
+int ao_oracle_generate_rays_for(const OrSamples* S, uint64_t k, uint64_t gid, int rays_per_sample, float offset,
+                                float maxdist, float* rays_out) {
+  const int q = sqrt_rays(rays_per_sample);
+  for (int px = 0; px < q; px++)
+    for (int py = 0; py < q; py++) {
+      Ray r = make_ray(*S, k, px, py, q, offset, maxdist, gid);
+      float* o = rays_out + (uint64_t)(px * q + py) * 8;
+      o[0] = r.o.x; o[1] = r.o.y; o[2] = r.o.z; o[3] = r.tmin;
+      o[4] = r.d.x; o[5] = r.d.y; o[6] = r.d.z; o[7] = r.tmax;
+    }
   return 0;
 }
 

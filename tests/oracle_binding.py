@@ -44,6 +44,7 @@ def lib():
         L.ao_oracle_trace_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int]
         L.ao_oracle_ray_margin.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         L.ao_oracle_generate_rays.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_float, C.c_float, C.c_void_p]
+        L.ao_oracle_generate_rays_for.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_float, C.c_float, C.c_void_p]
         L.ao_oracle_compute_ao.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_float,
                                            C.c_float, C.c_void_p, C.c_void_p]
         L.ao_oracle_filter_area.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -147,6 +148,14 @@ class Oracle:
         out = np.zeros((end - begin, q * q, 8), dtype=np.float32)
         lib().ao_oracle_generate_rays(samples.ref(), begin, end, rays_per_sample, float(offset), float(maxdist),
                                       out.ctypes.data)
+        return out
+
+    def generate_rays_for(self, samples: SampleBuffers, k, global_index, rays_per_sample, offset, maxdist):
+        """Rays of local sample k with the RNG streams of `global_index` (subset parity checks)."""
+        q = lib().ao_oracle_sqrt_rays(rays_per_sample)
+        out = np.zeros((q * q, 8), dtype=np.float32)
+        lib().ao_oracle_generate_rays_for(samples.ref(), k, global_index, rays_per_sample, float(offset), float(maxdist),
+                                          out.ctypes.data)
         return out
 
     def compute_ao(self, samples: SampleBuffers, rays_per_sample, offset, maxdist, begin=0, end=None):
