@@ -142,8 +142,12 @@ __global__ void k_morton(const F4* __restrict__ plo, const F4* __restrict__ phi,
   if (i >= n) return;
   const V3 cmin = v3(ordered_to_float(b6[0]), ordered_to_float(b6[1]), ordered_to_float(b6[2]));
   const V3 cmax = v3(ordered_to_float(b6[3]), ordered_to_float(b6[4]), ordered_to_float(b6[5]));
-  const V3 cinv = v3(cmax.x > cmin.x ? 1.0f / (cmax.x - cmin.x) : 0.f, cmax.y > cmin.y ? 1.0f / (cmax.y - cmin.y) : 0.f,
-                     cmax.z > cmin.z ? 1.0f / (cmax.z - cmin.z) : 0.f);
+  // one scale for all axes (cubical Morton cells): a thin axis — the height of a terrain — only
+  // gets split once the cells have shrunk to its extent, instead of wasting the top-level
+  // splits that per-axis normalisation would spend on it
+  const float ext = fmaxf(cmax.x - cmin.x, fmaxf(cmax.y - cmin.y, cmax.z - cmin.z));
+  const float inv = ext > 0.0f ? 1.0f / ext : 0.0f;
+  const V3 cinv = v3(inv, inv, inv);
   keys[i] = morton63(plo[i], phi[i], cmin, cinv);
   vals[i] = i;
 }
@@ -707,27 +711,29 @@ __global__ void k_ls_edges(const uint64_t* __restrict__ keys, const uint32_t* __
   E.c[3] = w * (-1.0 / h[1]);
   edges[atomicAdd(edge_count, 1u)] = E;
 }
-__global__ void k_ls_diag(const uint32_t* __restrict__ tris, uint64_t nT, const double* __restrict__ Mt, const LsEdge* __restrict__ edges,
-                          uint32_t nE, double w, double* __restrict__ diag) {
+// diagonal of the sampled mass matrix (lumped-mass test and the Jacobi preconditioner)
+__global__ void k_ls_diag_mass(const uint32_t* __restrict__ tris, uint64_t nT, const double* __restrict__ Mt, double* __restrict__ diag) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < nT) {
-    atomicAdd(&diag[tris[3 * i]], Mt[6 * i]);
-    atomicAdd(&diag[tris[3 * i + 1]], Mt[6 * i + 3]);
-    atomicAdd(&diag[tris[3 * i + 2]], Mt[6 * i + 5]);
-  }
-  if (i < nE) {
-    const LsEdge E = edges[i];
-    atomicAdd(&diag[E.i], w * E.c[0] * E.c[0]); atomicAdd(&diag[E.j], w * E.c[1] * E.c[1]);
-    atomicAdd(&diag[E.p], w * E.c[2] * E.c[2]); atomicAdd(&diag[E.q], w * E.c[3] * E.c[3]);
-  }
+  if (i >= nT) return;
+  const double a = Mt[6 * i], b = Mt[6 * i + 3], c = Mt[6 * i + 5];
+  if (a != 0.0) atomicAdd(&diag[tris[3 * i]], a);
+  if (b != 0.0) atomicAdd(&diag[tris[3 * i + 1]], b);
+  if (c != 0.0) atomicAdd(&diag[tris[3 * i + 2]], c);
 }
-// rows with zero diagonal: diag = 1, rhs = 0 (decision #7)
+// decision #7: vertices with zero lumped mass get M_vv = 1, rhs 0
 __global__ void k_ls_fix(double* __restrict__ diag, double* __restrict__ rhs, uint8_t* __restrict__ fixed, uint64_t nV) {
   const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= nV) return;
   const bool f = !(diag[v] > 0.0);
   fixed[v] = f ? 1 : 0;
   if (f) { diag[v] = 1.0; rhs[v] = 0.0; }
+}
+__global__ void k_ls_diag_edges(const LsEdge* __restrict__ edges, uint32_t nE, double w, double* __restrict__ diag) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nE) return;
+  const LsEdge E = edges[i];
+  atomicAdd(&diag[E.i], w * E.c[0] * E.c[0]); atomicAdd(&diag[E.j], w * E.c[1] * E.c[1]);
+  atomicAdd(&diag[E.p], w * E.c[2] * E.c[2]); atomicAdd(&diag[E.q], w * E.c[3] * E.c[3]);
 }
 // y += (M + w R) x   (y zeroed by the caller); one thread per triangle and per edge
 __global__ void k_ls_apply(const uint32_t* __restrict__ tris, uint64_t nT, const double* __restrict__ Mt, const LsEdge* __restrict__ edges,
@@ -754,7 +760,7 @@ __global__ void k_ls_apply(const uint32_t* __restrict__ tris, uint64_t nT, const
 }
 __global__ void k_ls_fix_apply(const uint8_t* __restrict__ fixed, const double* __restrict__ p, double* __restrict__ Ap, uint64_t nV) {
   const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (v < nV && fixed[v]) Ap[v] = p[v];
+  if (v < nV && fixed[v]) Ap[v] += p[v];
 }
 // out[slot] += sum a[i]*b[i]  (block reduce + one fp64 atomic per block)
 __global__ void k_dot(const double* __restrict__ a, const double* __restrict__ b, uint64_t n, double* __restrict__ out) {

@@ -945,9 +945,10 @@ int aobake_map_ao_to_vertices(AoBake* ctx, int mode, float weight, float* const*
         CK(cudaStreamSynchronize(st));
       }
       const uint64_t nwork = std::max<uint64_t>(nT, nE);
-      if (nwork) k_ls_diag<<<grid_for(nwork, 256), 256, 0, st>>>(m.tris.p, nT, Mt.p, edges.p, nE, w, diag.p);
+      if (nT) k_ls_diag_mass<<<grid_for(nT, 256), 256, 0, st>>>(m.tris.p, nT, Mt.p, diag.p);
+      if (nV) k_ls_fix<<<grid_for(nV, 256), 256, 0, st>>>(diag.p, rhs.p, fixed.p, nV);
+      if (nE) k_ls_diag_edges<<<grid_for(nE, 256), 256, 0, st>>>(edges.p, nE, w, diag.p);
       if (nV) {
-        k_ls_fix<<<grid_for(nV, 256), 256, 0, st>>>(diag.p, rhs.p, fixed.p, nV);
         k_ls_init<<<grid_for(nV, 256), 256, 0, st>>>(rhs.p, diag.p, r.p, z.p, p.p, x.p, nV);
       }
       CKL();

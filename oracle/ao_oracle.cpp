@@ -947,8 +947,8 @@ int ao_oracle_filter_area(const OrScene* sc, const uint64_t* per_instance, const
 // piecewise-linear interpolant across the edge (intrinsic/unfolded form):
 //   J = [(1-s1)/h1 + (1-s2)/h2] x_i + [s1/h1 + s2/h2] x_j - x_p/h1 - x_q/h2
 // (i,j) edge ends, p/q opposite vertices, h = altitude of the opposite vertex, s = foot
-// parameter along the edge.  Geometry uses world-space vertices.  Rows whose diagonal is
-// zero get diag 1, rhs 0.  Solver: Jacobi-preconditioned CG from x = 0 to
+// parameter along the edge.  Geometry uses world-space vertices.  Vertices with zero lumped
+// mass get M_vv = 1, rhs 0 (decision #7).  Solver: Jacobi-preconditioned CG from x = 0 to
 // |r|/|b| <= tol.  Returns iterations used (>= 0) or < 0 on error.
 struct LsEdge { uint32_t i, j, p, q; double c[4]; };
 
@@ -1044,13 +1044,16 @@ int ao_oracle_filter_least_squares(const OrScene* sc, const uint64_t* per_instan
       const uint32_t* idx = m.tri_vertex_indices + 3 * t;
       diag[idx[0]] += Mt[6 * t + 0]; diag[idx[1]] += Mt[6 * t + 3]; diag[idx[2]] += Mt[6 * t + 5];
     }
+    // decision #7: a vertex with zero lumped mass (no sample on any incident triangle) gets
+    // M_vv = 1, b_v = 0 — it is anchored at 0 like the averaging filter leaves it, and the
+    // system stays well conditioned when whole regions are unsampled (< 1 sample/triangle).
+    std::vector<uint8_t> fixed(nV, 0);
+    for (uint64_t v = 0; v < nV; v++)
+      if (!(diag[v] > 0.0)) { fixed[v] = 1; diag[v] = 1.0; b[v] = 0.0; }
     for (const LsEdge& E : edges) {
       diag[E.i] += w * E.c[0] * E.c[0]; diag[E.j] += w * E.c[1] * E.c[1];
       diag[E.p] += w * E.c[2] * E.c[2]; diag[E.q] += w * E.c[3] * E.c[3];
     }
-    std::vector<uint8_t> fixed(nV, 0);
-    for (uint64_t v = 0; v < nV; v++)
-      if (!(diag[v] > 0.0)) { fixed[v] = 1; diag[v] = 1.0; b[v] = 0.0; }
     std::vector<double> x(nV, 0.0), r(b), z(nV), p(nV), Ap(nV);
     double bnorm = 0.0;
     for (uint64_t v = 0; v < nV; v++) bnorm += b[v] * b[v];
@@ -1064,7 +1067,7 @@ int ao_oracle_filter_least_squares(const OrScene* sc, const uint64_t* per_instan
         for (uint64_t v = 0; v < nV; v++) rn += r[v] * r[v];
         if (std::sqrt(rn) <= tol * bnorm) break;
         apply(p, Ap);
-        for (uint64_t v = 0; v < nV; v++) if (fixed[v]) Ap[v] = p[v];
+        for (uint64_t v = 0; v < nV; v++) if (fixed[v]) Ap[v] += p[v];
         double pAp = 0.0;
         for (uint64_t v = 0; v < nV; v++) pAp += p[v] * Ap[v];
         if (!(pAp > 0.0)) break;

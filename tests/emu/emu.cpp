@@ -41,8 +41,9 @@ static uint32_t build_segment(const std::vector<F4>& plo, const std::vector<F4>&
     cmin = v3(fminf(cmin.x, cx), fminf(cmin.y, cy), fminf(cmin.z, cz));
     cmax = v3(fmaxf(cmax.x, cx), fmaxf(cmax.y, cy), fmaxf(cmax.z, cz));
   }
-  V3 cinv = v3(cmax.x > cmin.x ? 1.0f / (cmax.x - cmin.x) : 0.f, cmax.y > cmin.y ? 1.0f / (cmax.y - cmin.y) : 0.f,
-               cmax.z > cmin.z ? 1.0f / (cmax.z - cmin.z) : 0.f);
+  const float ext = fmaxf(cmax.x - cmin.x, fmaxf(cmax.y - cmin.y, cmax.z - cmin.z));
+  const float inv = ext > 0.0f ? 1.0f / ext : 0.0f;
+  V3 cinv = v3(inv, inv, inv);
   std::vector<uint64_t> keys(n);
   std::vector<uint32_t> order(n);
   for (uint32_t i = 0; i < n; i++) keys[i] = morton63(plo[i], phi[i], cmin, cinv);

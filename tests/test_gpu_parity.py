@@ -292,3 +292,24 @@ def test_full_size_config2_properties_and_subset_parity(api):
         ohits[k] = orc.trace_rays(r).sum()
     diff = np.abs(ohits.astype(np.int64) - hits[pick].astype(np.int64)).sum()
     assert 1.0 - diff / (len(pick) * rays) >= HIT_AGREEMENT
+
+
+def test_least_squares_with_unsampled_regions(api):
+    """< 1 sample per triangle (config 3/5 regime): the leftover rule leaves whole regions
+    unsampled; zero-lumped-mass vertices are anchored (decision #7) and CG converges quickly."""
+    scene, blockers = SCENES["warped_ground"]
+    off, maxd = scenes.default_distances(scene)
+    orc = Oracle(scene, blockers)
+    with api.Baker() as bk:
+        bk.set_scene(scene, blockers)
+        total, per = bk.distribute_samples(0, scene.num_triangles // 3)
+        sb = bk.sample_instances(per, 0)
+        ao = bk.compute_ao(64, off, maxd)
+        v_ls = bk.map_ao_to_vertices(api.FILTER_LEAST_SQUARES, 0.1)[0]
+        v_area = bk.map_ao_to_vertices(api.FILTER_AREA_BASED)[0]
+        iters = bk.timings().cg_iterations
+    o_ls = orc.filter_least_squares(sb, ao, 0.1, per_instance=per)[0]
+    o_area = orc.filter_area(sb, ao, per)[0]
+    assert np.abs(v_ls - o_ls).max() <= VERTEX_AO_TOL and np.abs(v_area - o_area).max() <= VERTEX_AO_TOL
+    assert (v_area == 0).mean() > 0.3          # a large unsampled region exists
+    assert iters < 500
