@@ -121,6 +121,7 @@ struct Lbvh {
   F4* ilo;                // [n-1] internal boxes
   F4* ihi;
   uint32_t* flags;        // [n-1] zeroed arrival counters
+  uint32_t* count;        // [n-1] primitives under each internal node
   uint32_t n;
 };
 
@@ -160,6 +161,7 @@ AOB_HD void lbvh_hierarchy_body(uint32_t tid, const Lbvh& L) {
   L.right[i] = rref;
   L.first[i] = (uint32_t)lo;
   L.last[i] = (uint32_t)hi;
+  L.count[i] = (uint32_t)(hi - lo + 1);
   if (i == 0) L.parent_int[0] = kSentinel;
 }
 
@@ -200,7 +202,7 @@ AOB_HD float box_half_area(F4 lo, F4 hi) {
   return dx * dy + dy * dz + dz * dx;
 }
 AOB_HD uint32_t lbvh_ref_count(const Lbvh& L, uint32_t ref) {
-  return (ref & kLeafBit) ? 1u : (L.last[ref] - L.first[ref] + 1u);
+  return (ref & kLeafBit) ? 1u : L.count[ref];
 }
 
 // smallest biased exponent e with 255 * 2^(e-127) >= extent (0 when extent == 0)
@@ -313,9 +315,15 @@ AOB_HD void collapse_body(uint32_t w, const CollapseArgs& A) {
       A.wide2bin[cbase + ci] = slot[k];
       ci++;
     } else {
-      const uint32_t cnt = lbvh_ref_count(L, slot[k]);
-      const uint32_t f = (slot[k] & kLeafBit) ? (slot[k] & ~kLeafBit) : L.first[slot[k]];
-      for (uint32_t c = 0; c < cnt; c++) A.leaf_prims[pbase + po + c] = L.prim[f + c];
+      // enumerate the (<= max_leaf) primitives of the subtree, depth first
+      uint32_t cnt = 0, st[8];
+      int sp = 0;
+      st[sp++] = slot[k];
+      while (sp) {
+        const uint32_t rr = st[--sp];
+        if (rr & kLeafBit) A.leaf_prims[pbase + po + cnt++] = L.prim[rr & ~kLeafBit];
+        else { st[sp++] = L.right[rr]; st[sp++] = L.left[rr]; }
+      }
       nd.meta[k] = (uint8_t)((((1u << cnt) - 1u) << 5) | po);
       po += cnt;
     }

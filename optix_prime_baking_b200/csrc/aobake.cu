@@ -179,13 +179,13 @@ int build_segment(AoBake* ctx, const F4* d_plo, const F4* d_phi, uint32_t n, uin
   DBuf<int> d_b;  // 6 centroid + 6 box bounds
   DBuf<float> d_box;
   DBuf<uint64_t> keys, keys_s;
-  DBuf<uint32_t> vals, vals_s, left, right, first, last, pint, pleaf, flags, wide2bin, counters;
+  DBuf<uint32_t> vals, vals_s, left, right, first, last, pint, pleaf, flags, wide2bin, counters, count;
   DBuf<F4> ilo, ihi;
   const uint32_t ni = n > 1 ? n - 1 : 1;
   CK(d_b.alloc(12)); CK(d_box.alloc(6));
   CK(keys.alloc(n)); CK(keys_s.alloc(n)); CK(vals.alloc(n)); CK(vals_s.alloc(n));
   CK(left.alloc(ni)); CK(right.alloc(ni)); CK(first.alloc(ni)); CK(last.alloc(ni)); CK(pint.alloc(ni)); CK(pleaf.alloc(n));
-  CK(flags.alloc(ni)); CK(wide2bin.alloc(n)); CK(counters.alloc(2)); CK(ilo.alloc(ni)); CK(ihi.alloc(ni));
+  CK(flags.alloc(ni)); CK(count.alloc(ni)); CK(wide2bin.alloc(n)); CK(counters.alloc(2)); CK(ilo.alloc(ni)); CK(ihi.alloc(ni));
   k_init_bounds<<<1, 32, 0, st>>>(d_b.p);
   k_init_bounds<<<1, 32, 0, st>>>(d_b.p + 6);
   k_bounds<<<std::min<unsigned>(grid_for(n, 256), 148u * 8u), 256, 0, st>>>(d_plo, d_phi, n, d_b.p, d_b.p + 6);
@@ -203,7 +203,7 @@ int build_segment(AoBake* ctx, const F4* d_plo, const F4* d_phi, uint32_t n, uin
   Lbvh L;
   L.keys = keys_s.p; L.prim = vals_s.p; L.plo = d_plo; L.phi = d_phi;
   L.left = left.p; L.right = right.p; L.first = first.p; L.last = last.p;
-  L.parent_int = pint.p; L.parent_leaf = pleaf.p; L.ilo = ilo.p; L.ihi = ihi.p; L.flags = flags.p; L.n = n;
+  L.parent_int = pint.p; L.parent_leaf = pleaf.p; L.ilo = ilo.p; L.ihi = ihi.p; L.flags = flags.p; L.count = count.p; L.n = n;
   if (n >= 2) {
     CK(cudaMemsetAsync(flags.p, 0, ni * sizeof(uint32_t), st));
     k_hierarchy<<<grid_for(n - 1, 256), 256, 0, st>>>(L);

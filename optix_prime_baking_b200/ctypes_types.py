@@ -55,7 +55,7 @@ class PackedScene:
             cm.normal_stride_bytes = m.normals.strides[0] if m.normals is not None else 0
             cm.num_triangles = len(m.tris)
             cm.tri_vertex_indices = m.tris.ctypes.data
-            lo, hi = m.bbox if len(m.vertices) else (np.zeros(3), np.zeros(3))
+            lo, hi = m.bbox
             cm.bbox_min[:] = [float(x) for x in lo]
             cm.bbox_max[:] = [float(x) for x in hi]
         for k, inst in enumerate(scene.instances):

@@ -25,7 +25,10 @@ class Mesh:
 
     @property
     def bbox(self):
-        return self.vertices.min(axis=0), self.vertices.max(axis=0)
+        if getattr(self, "_bbox", None) is None:
+            self._bbox = (self.vertices.min(axis=0), self.vertices.max(axis=0)) if len(self.vertices) else \
+                (np.zeros(3, np.float32), np.zeros(3, np.float32))
+        return self._bbox
 
 
 @dataclass

@@ -52,13 +52,14 @@ static uint32_t build_segment(const std::vector<F4>& plo, const std::vector<F4>&
   std::vector<uint64_t> skeys(n);
   for (uint32_t i = 0; i < n; i++) skeys[i] = keys[order[i]];
   const uint32_t ni = n > 1 ? n - 1 : 1;
-  std::vector<uint32_t> left(ni), right(ni), first(ni), last(ni), pint(ni), pleaf(n), flags(ni, 0), wide2bin(n);
+  std::vector<uint32_t> left(ni), right(ni), first(ni), last(ni), pint(ni), pleaf(n), flags(ni, 0), wide2bin(n), count(ni, 0);
   std::vector<F4> ilo(ni), ihi(ni);
   Lbvh L;
   L.keys = skeys.data(); L.prim = order.data(); L.plo = plo.data(); L.phi = phi.data();
   L.left = left.data(); L.right = right.data(); L.first = first.data(); L.last = last.data();
   L.parent_int = pint.data(); L.parent_leaf = pleaf.data(); L.ilo = ilo.data(); L.ihi = ihi.data();
-  L.flags = flags.data(); L.n = n;
+  L.flags = flags.data(); L.count = count.data(); L.n = n;
+  const uint32_t root_ref = (n == 1) ? (0u | kLeafBit) : 0u;
   for (uint32_t i = 0; i + 1 < n; i++) lbvh_hierarchy_body(i, L);
   for (uint32_t i = 0; i < n; i++) lbvh_refit_body(i, L);
   nodes.resize(node_offset + n);
@@ -67,7 +68,7 @@ static uint32_t build_segment(const std::vector<F4>& plo, const std::vector<F4>&
   A.L = L; A.nodes = nodes.data(); A.wide2bin = wide2bin.data(); A.leaf_prims = leaf_prims.data();
   A.node_count = &node_count; A.prim_count = &prim_count; A.node_offset = node_offset; A.prim_offset = prim_offset;
   A.max_leaf = max_leaf;
-  wide2bin[0] = (n == 1) ? (0u | kLeafBit) : 0u;
+  wide2bin[0] = root_ref;
   uint32_t lb = 0, le = 1;
   while (lb < le) {
     for (uint32_t w = lb; w < le; w++) collapse_body(w, A);
