@@ -356,8 +356,39 @@ AOB_HD void ray_setup(RayState& r, V3 org, V3 dir, float tmin, float tmax) {
   r.idir = v3(safe_rcp(dir.x), safe_rcp(dir.y), safe_rcp(dir.z));
 }
 
-AOB_D float q2f(uint32_t word, int k, uint32_t k47 = 0x47000000u) {  // 32768 + byte k of word, as float (no int->float convert)
-  return as_float(byte_perm(word, k47, 0x7404u | ((uint32_t)k << 4)));
+// Constants of the node test, pinned in registers once per thread: ptxas otherwise re-materialises
+// the PRMT selectors from uniform registers with a MOV in front of every PRMT (22 MOVs per node on
+// the binding ALU pipe).
+struct NodeConsts {
+  uint32_t k47;     // 0x47000000 = 32768.0f
+};
+#if defined(__CUDACC__)
+// 32768.0f lives in the constant bank on purpose.  PRMT takes one immediate; when both the
+// selector and 0x47000000 are compile-time constants ptxas keeps one of them in a scratch
+// register that the PRMT itself overwrites and re-materialises it with a MOV before every one of
+// the 48 PRMTs of a node test — on the binding ALU pipe.  Read from c[], the value is opaque,
+// stays in one register (or is used as a constant-bank operand), and the selectors are immediates.
+__constant__ uint32_t c_k47 = 0x47000000u;
+#endif
+AOB_D NodeConsts make_node_consts() {
+  NodeConsts c;
+#if defined(__CUDA_ARCH__)
+  c.k47 = c_k47;
+#else
+  c.k47 = 0x47000000u;
+#endif
+  return c;
+}
+AOB_D float q2f(uint32_t word, int k, const NodeConsts& c) {  // 32768 + byte k of word, as float (no int->float convert)
+  return as_float(byte_perm(word, c.k47, 0x7404u | ((uint32_t)k << 4)));
+}
+// (hi << 1) | (lo >> 31): shifts the sign bit of `lo` into an accumulator with one SHF
+AOB_D uint32_t shift_in_sign(uint32_t acc, uint32_t lo) {
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_l(lo, acc, 1);
+#else
+  return (acc << 1) | (lo >> 31);
+#endif
 }
 
 // Slab-tests the 8 quantised child boxes of node `idx`; returns the hit mask in the layout
@@ -369,7 +400,7 @@ AOB_D float q2f(uint32_t word, int k, uint32_t k47 = 0x47000000u) {  // 32768 + 
 // constant o and of the final FMA is bounded by 5e-7*|b| + 0.008*|ad|; near/far are pushed
 // apart by pad = 1e-6*|b| + 0.0234*|ad| (2.3 % of one quantisation step), so a box the exact
 // ray touches is never culled and no per-child padding multiply is needed.
-AOB_D uint32_t intersect_node8(const U4* nodes, uint32_t idx, const RayState& r, uint32_t* child_base,
+AOB_D uint32_t intersect_node8(const U4* nodes, uint32_t idx, const RayState& r, const NodeConsts& nc, uint32_t* child_base,
                                uint32_t* prim_base, uint32_t* imask) {
   const U4* p = nodes + 5ull * idx;
   const U4 n0 = ld_u4(p), n1 = ld_u4(p + 1), n2 = ld_u4(p + 2), n3 = ld_u4(p + 3), n4 = ld_u4(p + 4);
@@ -389,28 +420,28 @@ AOB_D uint32_t intersect_node8(const U4* nodes, uint32_t idx, const RayState& r,
   const float padz = fmaf(0.0234375f, fabsf(adz), 1.0e-6f * fabsf(bz));
   const float onx = ox - padx, ofx = ox + padx, ony = oy - pady, ofy = oy + pady, onz = oz - padz, ofz = oz + padz;
   const bool nx = r.dir.x < 0.0f, ny = r.dir.y < 0.0f, nz = r.dir.z < 0.0f;
-  uint32_t hb = 0;
-  uint32_t k47 = 0x47000000u;
-#if defined(__CUDA_ARCH__)
-  asm volatile("mov.b32 %0, 0x47000000;" : "=r"(k47));  // keep the PRMT constant in one register (no re-materialising MOVs)
-#endif
+  // Children are tested from slot 7 down to slot 0; each pushes the sign bit of (tf - tn) into
+  // `miss` (one FADD on the FMA pipe + one SHF), so slot s ends up in bit s and a set bit means
+  // "missed" (tf < tn).  tf - tn is never NaN (all operands finite) and x - x = +0.
+  uint32_t miss = 0;
 #pragma unroll
-  for (int h = 0; h < 2; h++) {
+  for (int h = 1; h >= 0; h--) {
     const uint32_t lox = h ? n2.y : n2.x, loy = h ? n2.w : n2.z, loz = h ? n3.y : n3.x;
     const uint32_t hix = h ? n3.w : n3.z, hiy = h ? n4.y : n4.x, hiz = h ? n4.w : n4.z;
     const uint32_t nwx = nx ? hix : lox, fwx = nx ? lox : hix;
     const uint32_t nwy = ny ? hiy : loy, fwy = ny ? loy : hiy;
     const uint32_t nwz = nz ? hiz : loz, fwz = nz ? loz : hiz;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const float tnx = fmaf(q2f(nwx, k, k47), adx, onx), tfx = fmaf(q2f(fwx, k, k47), adx, ofx);
-      const float tny = fmaf(q2f(nwy, k, k47), ady, ony), tfy = fmaf(q2f(fwy, k, k47), ady, ofy);
-      const float tnz = fmaf(q2f(nwz, k, k47), adz, onz), tfz = fmaf(q2f(fwz, k, k47), adz, ofz);
+    for (int k = 3; k >= 0; k--) {
+      const float tnx = fmaf(q2f(nwx, k, nc), adx, onx), tfx = fmaf(q2f(fwx, k, nc), adx, ofx);
+      const float tny = fmaf(q2f(nwy, k, nc), ady, ony), tfy = fmaf(q2f(fwy, k, nc), ady, ofy);
+      const float tnz = fmaf(q2f(nwz, k, nc), adz, onz), tfz = fmaf(q2f(fwz, k, nc), adz, ofz);
       const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, r.tmin));
       const float tf = fminf(fminf(tfx, tfy), fminf(tfz, r.tmax));
-      if (tn <= tf) hb |= 1u << (4 * h + k);
+      miss = shift_in_sign(miss, as_uint(tf - tn));
     }
   }
+  const uint32_t hb = ~miss & 0xffu;
   // expand the 8 slot bits: internal slots map to bits 24+slot; leaf slots to their primitive bits
   uint32_t hitmask = (hb & im) << 24;
   uint32_t lh = hb & ~im;
@@ -456,6 +487,7 @@ template <bool STATS>
 AOB_D bool trace_any_hit(const BvhView& bvh, V3 org, V3 dir, float tmin, float tmax, U2* stack, TraceCounters* cnt) {
   RayState r;
   ray_setup(r, org, dir, tmin, tmax);
+  const NodeConsts nc = make_node_consts();
   int sp = 0;
   bool in_blas = !bvh.two_level;
   U2 G;
@@ -470,7 +502,7 @@ AOB_D bool trace_any_hit(const BvhView& bvh, V3 org, V3 dir, float tmin, float t
       const uint32_t node = G.x + (uint32_t)popc32(G.y & 0xffu & ((1u << slot) - 1u));
       if (G.y & 0xff000000u) stack[sp++] = G;
       uint32_t cb, pb, im;
-      const uint32_t hm = intersect_node8(bvh.nodes, node, r, &cb, &pb, &im);
+      const uint32_t hm = intersect_node8(bvh.nodes, node, r, nc, &cb, &pb, &im);
       if (STATS) cnt->nodes++;
       G.x = cb; G.y = (hm & 0xff000000u) | im;
       T.x = pb; T.y = hm & 0x00ffffffu;

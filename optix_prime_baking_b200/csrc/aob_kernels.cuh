@@ -435,8 +435,9 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
     return sp < kSmStack ? s_stack[sp][threadIdx.x] : l_stack[sp - kSmStack];
   };
 
+  const NodeConsts nc = make_node_consts();
   // per-lane item state
-  __shared__ float s_la[3][kAoBlock];  // queued (lookahead) ray direction per thread
+  __shared__ float s_la[6][kAoBlock];  // queued (lookahead) ray per thread: direction + slab reciprocals
   bool la_valid = false;
   bool have_item = false, ray_active = false, exhausted = false;
   uint32_t rel = 0, pass = 0, pass_end = 0, nh = 0;
@@ -460,7 +461,7 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
     wdir = v3(s_la[0][threadIdx.x], s_la[1][threadIdx.x], s_la[2][threadIdx.x]);
     la_valid = false;
     r.org = org; r.dir = wdir;
-    r.idir = v3(safe_rcp(wdir.x), safe_rcp(wdir.y), safe_rcp(wdir.z));
+    r.idir = v3(s_la[3][threadIdx.x], s_la[4][threadIdx.x], s_la[5][threadIdx.x]);
     in_blas = !TWO_LEVEL;
     G.x = bvh.root;
     G.y = (1u << 24) | 1u;
@@ -521,6 +522,7 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
       const V3 d = ao_ray_dir((uint32_t)(begin + rel), pass, q, nrm, fnrm, onb);
       pass++;
       s_la[0][threadIdx.x] = d.x; s_la[1][threadIdx.x] = d.y; s_la[2][threadIdx.x] = d.z;
+      s_la[3][threadIdx.x] = safe_rcp(d.x); s_la[4][threadIdx.x] = safe_rcp(d.y); s_la[5][threadIdx.x] = safe_rcp(d.z);
       la_valid = true;
     }
     if (!ray_active && la_valid) start_queued();
@@ -541,7 +543,7 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
           const uint32_t node = G.x + (uint32_t)__popc(G.y & 0xffu & ((1u << slot) - 1u));
           if (G.y & 0xff000000u) push(sp, G);
           uint32_t cb, pb, im;
-          const uint32_t hm = intersect_node8(bvh.nodes, node, r, &cb, &pb, &im);
+          const uint32_t hm = intersect_node8(bvh.nodes, node, r, nc, &cb, &pb, &im);
           if (STATS) c_nodes++;
           G.x = cb; G.y = (hm & 0xff000000u) | im;
           T.x = pb; T.y = hm & 0x00ffffffu;
