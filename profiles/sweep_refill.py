@@ -6,7 +6,7 @@ import bench
 scene, blockers, min_per, requested, desc = bench.make_workload(w)
 rays=bench.RAYS[w]
 off,maxd=scenes.default_distances(scene)
-for tk, rb in [(1,0),(2,28),(2,30),(2,32)]:
+for tk, rb in [(2,30)]:
     with api.Baker(trace_kernel=tk, refill_below=rb) as bk:
         bk.set_scene(scene, blockers)
         total, per = bk.distribute_samples(min_per, requested)
