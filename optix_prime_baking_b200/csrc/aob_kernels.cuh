@@ -579,17 +579,13 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
             G.y = (1u << 24) | 1u;
           }
         }
-        if (hit) {
-          nh++;
-          ray_active = false;
-          if (la_valid) start_queued();
-        } else if ((G.y & 0xff000000u) == 0u) {
+        // Ray end and restart are written once, straight-line: lanes ending on a hit, lanes ending
+        // on an empty stack and lanes that merely pop all run the same short sequence instead of
+        // three serialised divergent copies.
+        bool done = hit;
+        if (!hit && (G.y & 0xff000000u) == 0u) {
           while (true) {
-            if (sp == 0) {
-              ray_active = false;
-              if (la_valid) start_queued();
-              break;
-            }
+            if (sp == 0) { done = true; break; }
             G = pop(sp);
             if (TWO_LEVEL && G.x == kSentinel && G.y == 0u) {
               r.org = org; r.dir = wdir;
@@ -599,6 +595,11 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
             }
             break;
           }
+        }
+        nh += hit ? 1u : 0u;
+        if (done) {
+          ray_active = false;
+          if (la_valid) start_queued();
         }
       }
       const uint32_t act = __ballot_sync(0xffffffffu, ray_active);
