@@ -472,9 +472,29 @@ AOB_D bool test_tri_group_k(const F4* tris, uint32_t base, uint32_t mask, V3 org
   } while (mask);
   return false;
 }
+AOB_D bool test_tri_group_sel(const F4* tris, uint32_t base, uint32_t mask, V3 org, const Shear& sh, float tmin, float tmax,
+                              uint32_t* tested) {
+  do {
+    const int b = ffs32(mask) - 1;
+    mask &= mask - 1u;
+    const uint64_t prim = (uint64_t)base + (uint32_t)b;
+    const F4 a = ld_f4(tris + 3 * prim), bb = ld_f4(tris + 3 * prim + 1), c = ld_f4(tris + 3 * prim + 2);
+    (*tested)++;
+    if (woop_hit_sel(org, sh, tmin, tmax, v3(a.x, a.y, a.z), v3(bb.x, bb.y, bb.z), v3(c.x, c.y, c.z))) return true;
+  } while (mask);
+  return false;
+}
 // The Woop shear constants are only needed by rays that reach a triangle: computed here, lazily.
+// When every lane of the warp that is in a triangle test right now has the same dominant axis
+// the select-free copy for that axis runs (a warp-uniform branch); otherwise one select-based
+// copy serves all of them instead of up to three serialised specialised ones.
 AOB_D bool test_tri_group(const F4* tris, uint32_t base, uint32_t mask, V3 org, V3 dir, float tmin, float tmax, uint32_t* tested) {
   const Shear sh = make_shear(dir);
+#if defined(__CUDA_ARCH__)
+  const unsigned am = __activemask();
+  const int kz0 = __shfl_sync(am, sh.kz, __ffs((int)am) - 1);
+  if (!__all_sync(am, sh.kz == kz0)) return test_tri_group_sel(tris, base, mask, org, sh, tmin, tmax, tested);
+#endif
   switch (sh.kz) {
     case 0: return test_tri_group_k<0>(tris, base, mask, org, sh, tmin, tmax, tested);
     case 1: return test_tri_group_k<1>(tris, base, mask, org, sh, tmin, tmax, tested);

@@ -248,6 +248,36 @@ AOB_HD bool woop_hit_k(V3 org, const Shear& s, float tmin, float tmax, V3 p0, V3
   const float Ts = det < 0.0f ? -T : T;
   return (Ts > ex::mul(tmin, ad)) && (Ts < ex::mul(tmax, ad));
 }
+// Same test with the axis permutation done by selects (branch-free): identical arithmetic after
+// the selection, so identical decisions.  Used when the lanes of a warp that are in a triangle
+// test at the same time disagree on kz — one select path then beats up to three serialised
+// specialised copies.
+AOB_HD bool woop_hit_sel(V3 org, const Shear& s, float tmin, float tmax, V3 p0, V3 p1, V3 p2) {
+  const V3 A = sub(p0, org), B = sub(p1, org), C = sub(p2, org);
+  const bool z0 = s.kz == 0, z1 = s.kz == 1;
+  const float Akz = z0 ? A.x : (z1 ? A.y : A.z), Akx = z0 ? A.y : (z1 ? A.z : A.x), Aky = z0 ? A.z : (z1 ? A.x : A.y);
+  const float Bkz = z0 ? B.x : (z1 ? B.y : B.z), Bkx = z0 ? B.y : (z1 ? B.z : B.x), Bky = z0 ? B.z : (z1 ? B.x : B.y);
+  const float Ckz = z0 ? C.x : (z1 ? C.y : C.z), Ckx = z0 ? C.y : (z1 ? C.z : C.x), Cky = z0 ? C.z : (z1 ? C.x : C.y);
+  const float Ax = ex::sub(Akx, ex::mul(s.Sx, Akz)), Ay = ex::sub(Aky, ex::mul(s.Sy, Akz));
+  const float Bx = ex::sub(Bkx, ex::mul(s.Sx, Bkz)), By = ex::sub(Bky, ex::mul(s.Sy, Bkz));
+  const float Cx = ex::sub(Ckx, ex::mul(s.Sx, Ckz)), Cy = ex::sub(Cky, ex::mul(s.Sy, Ckz));
+  float U = ex::sub(ex::mul(Cx, By), ex::mul(Cy, Bx));
+  float V = ex::sub(ex::mul(Ax, Cy), ex::mul(Ay, Cx));
+  float W = ex::sub(ex::mul(Bx, Ay), ex::mul(By, Ax));
+  if (U == 0.0f || V == 0.0f || W == 0.0f) {
+    U = (float)ex::dsub(ex::dmul((double)Cx, (double)By), ex::dmul((double)Cy, (double)Bx));
+    V = (float)ex::dsub(ex::dmul((double)Ax, (double)Cy), ex::dmul((double)Ay, (double)Cx));
+    W = (float)ex::dsub(ex::dmul((double)Bx, (double)Ay), ex::dmul((double)By, (double)Ax));
+  }
+  if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+  const float det = ex::add(ex::add(U, V), W);
+  if (det == 0.0f) return false;
+  const float Az = ex::mul(s.Sz, Akz), Bz = ex::mul(s.Sz, Bkz), Cz = ex::mul(s.Sz, Ckz);
+  const float T = ex::add(ex::add(ex::mul(U, Az), ex::mul(V, Bz)), ex::mul(W, Cz));
+  const float ad = fabsf(det);
+  const float Ts = det < 0.0f ? -T : T;
+  return (Ts > ex::mul(tmin, ad)) && (Ts < ex::mul(tmax, ad));
+}
 AOB_HD bool woop_hit(V3 org, const Shear& s, float tmin, float tmax, V3 p0, V3 p1, V3 p2) {
   switch (s.kz) {
     case 0: return woop_hit_k<0>(org, s, tmin, tmax, p0, p1, p2);

@@ -180,6 +180,22 @@ uint64_t emu_trace(void* h, const float* rays, uint64_t n, uint8_t* hit, uint64_
   return nodes;
 }
 
+// select-based vs axis-specialised Woop test must agree bit for bit
+int emu_woop_variants_agree(const float* rays, uint64_t n, const float* tris9, uint64_t nt) {
+  int bad = 0;
+  for (uint64_t i = 0; i < n; i++) {
+    const float* p = rays + 8 * i;
+    const V3 o = v3(p[0], p[1], p[2]), d = v3(p[4], p[5], p[6]);
+    const Shear sh = make_shear(d);
+    for (uint64_t t = 0; t < nt; t++) {
+      const float* q = tris9 + 9 * t;
+      const V3 a = v3(q[0], q[1], q[2]), b = v3(q[3], q[4], q[5]), c = v3(q[6], q[7], q[8]);
+      if (woop_hit(o, sh, p[3], p[7], a, b, c) != woop_hit_sel(o, sh, p[3], p[7], a, b, c)) bad++;
+    }
+  }
+  return bad;
+}
+
 // ---- math parity hooks ----
 uint32_t emu_tea(uint32_t rounds, uint32_t v0, uint32_t v1) {
   switch (rounds) { case 2: return tea<2>(v0, v1); case 4: return tea<4>(v0, v1); case 16: return tea<16>(v0, v1); default: return 0; }

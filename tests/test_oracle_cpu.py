@@ -245,3 +245,13 @@ def test_ground_plane_matches_host_helper():
         assert np.allclose(v, g.vertices) and np.array_equal(t, g.tris)
         n = np.cross(v[t[0, 1]] - v[t[0, 0]], v[t[0, 2]] - v[t[0, 0]])
         assert (n[up % 3] > 0) == (up < 3)               # faces the scene
+
+
+def test_woop_variants_agree_bit_for_bit(emu):
+    """The axis-specialised and the select-based Woop tests (chosen per warp on the GPU) make
+    identical decisions for every (ray, triangle) pair."""
+    emu.emu_woop_variants_agree.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+    sc, bl = scenes.config1_sphere(12, 12)
+    wt = _world_tris([sc, bl])
+    rays = _random_rays(sc, 2000, 9)
+    assert emu.emu_woop_variants_agree(rays.ctypes.data, len(rays), wt.ctypes.data, len(wt)) == 0
