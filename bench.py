@@ -233,14 +233,21 @@ def main():
     # weak scaling: N x the single-GPU sample budget over the same (replicated) scene
     total, per = bk.distribute_samples(min_per, base_total * n_gpus) if n_gpus > 1 else bk.distribute_samples(min_per, requested)
     bk.sample_instances(per, min_per, download=False)
-    begin, end = rank * total // n_gpus, (rank + 1) * total // n_gpus
-    rays_rank = (end - begin) * q * q
+    begin, end = rank * total // n_gpus, (rank + 1) * total // n_gpus   # host-buffer (e2e) shards: contiguous
+    block_samples = 65536
     st = bk.stats()
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     def step():
-        bk.compute_ao(rays, off, maxd, download=False, begin=begin, end=end)
+        # resident path: interleaved 64k-sample super-blocks (even load across ranks), no collective
+        if n_gpus > 1:
+            bk.compute_ao_interleaved(rank, n_gpus, rays, off, maxd, block_samples)
+        else:
+            bk.compute_ao(rays, off, maxd, download=False)
+
+    step()
+    rays_rank = int(bk.timings().rays_traced)
 
     def barrier():
         torch.cuda.synchronize()
@@ -366,7 +373,7 @@ def main():
                        "samples_total": int(total), "rays_per_step": int(rays_job),
                        "bvh": f"{st.num_bvh_nodes} 8-wide nodes + {st.num_bvh_triangles} tris = {st.bvh_bytes / 1e6:.1f} MB, "
                               f"{'TLAS/BLAS' if st.two_level else 'flattened'}, replicated per GPU",
-                       "sharding": "contiguous global sample ranges, no data-path collective",
+                       "sharding": "interleaved 64k-sample super-blocks per rank (value); contiguous host shards (e2e); no data-path collective",
                        "l2": "256 MB flush write between timed iterations; BVH + samples exceed the 126 MB L2",
                        "trace_kernel": args.trace_kernel},
             "clocks": clocks,

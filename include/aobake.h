@@ -184,6 +184,13 @@ int aobake_compute_ao(AoBake* ctx, int rays_per_sample, float scene_offset, floa
  * host_ao nullable, (end - begin) floats. */
 int aobake_compute_ao_range(AoBake* ctx, size_t begin, size_t end, int rays_per_sample, float scene_offset,
                             float scene_maxdistance, float* host_ao);
+/* Interleaved multi-GPU partition of the whole sample set: this call traces the super-blocks of
+ * block_samples samples (multiple of 32; 0 => 65536) whose index % num_parts == part, and sets the
+ * resident ao[] of every other sample to 0 — a sum all-reduce over the parts then assembles the
+ * full array exactly.  Interleaving evens out regions of different traversal cost (the contiguous
+ * ranges of aobake_compute_ao_range can differ by 10-15 % on a terrain). */
+int aobake_compute_ao_interleaved(AoBake* ctx, uint32_t part, uint32_t num_parts, uint32_t block_samples,
+                                  int rays_per_sample, float scene_offset, float scene_maxdistance);
 /* Device pointer to the resident ao[num_samples] array (for an NCCL all-gather by the caller). */
 int aobake_get_ao_device(AoBake* ctx, float** d_ao, size_t* num_samples);
 /* Replace the resident AO array from the host (num_samples floats). */

@@ -28,7 +28,7 @@ _LIB = None
 EXPORTS = [
     "aobake_default_params", "aobake_create", "aobake_destroy", "aobake_last_error", "aobake_set_stream",
     "aobake_synchronize", "aobake_set_scene", "aobake_distribute_samples", "aobake_sample_instances",
-    "aobake_set_samples", "aobake_compute_ao", "aobake_compute_ao_range", "aobake_get_ao_device", "aobake_set_ao",
+    "aobake_set_samples", "aobake_compute_ao", "aobake_compute_ao_range", "aobake_compute_ao_interleaved", "aobake_get_ao_device", "aobake_set_ao",
     "aobake_map_ao_to_vertices", "aobake_make_ground_plane", "aobake_trace_rays", "aobake_dump_rays",
     "aobake_get_hit_counts", "aobake_get_timings", "aobake_get_stats", "aobake_num_samples",
 ]
@@ -85,6 +85,7 @@ def load_library(path: Optional[str] = None):
     L.aobake_set_samples.argtypes = [vp, vp, vp]
     L.aobake_compute_ao.argtypes = [vp, i32, f32, f32, vp]
     L.aobake_compute_ao_range.argtypes = [vp, sz, sz, i32, f32, f32, vp]
+    L.aobake_compute_ao_interleaved.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, i32, f32, f32]
     L.aobake_get_ao_device.argtypes = [vp, C.POINTER(vp), C.POINTER(sz)]
     L.aobake_set_ao.argtypes = [vp, vp]
     L.aobake_map_ao_to_vertices.argtypes = [vp, i32, f32, vp]
@@ -118,6 +119,7 @@ class Baker:
         p.device, p.instancing_mode, p.collect_stats = device, instancing_mode, int(collect_stats)
         p.cg_tolerance, p.cg_max_iterations, p.trace_kernel = cg_tolerance, cg_max_iterations, trace_kernel
         p.refill_below = refill_below
+        self.device = device
         self._h = C.c_void_p()
         rc = self.lib.aobake_create(C.byref(p), C.byref(self._h))
         if rc != 0:
@@ -201,6 +203,21 @@ class Baker:
         self._ck(self.lib.aobake_compute_ao_range(self._h, b, e, rays_per_sample, float(scene_offset),
                                                   float(scene_maxdistance), ao.ctypes.data if ao is not None else None))
         return ao
+
+    def compute_ao_interleaved(self, part: int, num_parts: int, rays_per_sample: int, scene_offset: float,
+                               scene_maxdistance: float, block_samples: int = 0):
+        """Trace the super-blocks owned by `part` of `num_parts`; other samples' AO is set to 0."""
+        self._ck(self.lib.aobake_compute_ao_interleaved(self._h, part, num_parts, block_samples, rays_per_sample,
+                                                        float(scene_offset), float(scene_maxdistance)))
+
+    def download_ao(self) -> np.ndarray:
+        import ctypes as _C
+        out = np.empty(self.num_samples, dtype=np.float32)
+        ptr, n = self.ao_device_ptr()
+        if n:
+            from .multi_gpu import device_tensor
+            out[...] = device_tensor(ptr, n, self.device).cpu().numpy()
+        return out
 
     def ao_device_ptr(self):
         p, n = C.c_void_p(), C.c_size_t()

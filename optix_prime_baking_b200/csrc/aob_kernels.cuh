@@ -418,6 +418,7 @@ constexpr int kSmStack = 12;
 template <bool STATS, bool TWO_LEVEL>
 __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleView S, uint64_t begin, uint32_t n, int q, float offset,
                                                              float maxdist, uint32_t n_chunks, uint32_t refill_below,
+                                                             uint32_t part, uint32_t num_parts, uint32_t sb_blocks, uint32_t n_local_blocks,
                                                              uint32_t* __restrict__ hits, unsigned long long* __restrict__ counter,
                                                              unsigned long long* __restrict__ stats) {
   __shared__ U2 s_stack[kSmStack][kAoBlock];
@@ -455,7 +456,11 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
   G.x = 0; G.y = 0;
   int sp = 0;
   uint32_t c_nodes = 0, c_tris = 0, c_insts = 0;
-  const unsigned long long n_blocks = ((unsigned long long)n + 31ull) / 32ull;
+  // Multi-GPU interleave: this launch owns the super-blocks sb (of sb_blocks 32-sample blocks) with
+  // sb % num_parts == part; local block k maps to global block ((k / sb_blocks) * num_parts + part)
+  // * sb_blocks + k % sb_blocks.  num_parts == 1 is the identity.
+  const unsigned long long n_blocks = n_local_blocks;
+  const unsigned long long n_global_blocks = ((unsigned long long)n + 31ull) / 32ull;
   const unsigned long long total_items = n_blocks * n_chunks;  // item = (block of 32 samples, strata chunk)
   auto start_queued = [&]() {
     wdir = v3(s_la[0][threadIdx.x], s_la[1][threadIdx.x], s_la[2][threadIdx.x]);
@@ -491,7 +496,9 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
         w = __shfl_sync(0xffffffffu, w, 0);
         if (w >= total_items) { exhausted = true; break; }
         supply_chunk = (uint32_t)(w / n_blocks);  // chunk-major: concurrent warps work on neighbouring blocks
-        const unsigned long long blk = w - (unsigned long long)supply_chunk * n_blocks;
+        unsigned long long blk = w - (unsigned long long)supply_chunk * n_blocks;
+        if (num_parts > 1) blk = ((blk / sb_blocks) * num_parts + part) * sb_blocks + blk % sb_blocks;
+        if (blk >= n_global_blocks) continue;  // padding block of a partial last super-block
         supply_next = (uint32_t)(blk * 32ull);
         supply_left = (uint32_t)min(32ull, (unsigned long long)n - blk * 32ull);
       }
@@ -618,10 +625,14 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
   }
 }
 
-__global__ void k_ao_finalize(const uint32_t* __restrict__ hits, uint64_t n, float denom, float* __restrict__ ao) {
+// ao = 1 - hits/q^2 for the samples this launch owns; 0 for the others (interleaved multi-GPU
+// partition), so that a sum all-reduce assembles the full array exactly (x + 0 + ... + 0 = x).
+__global__ void k_ao_finalize(const uint32_t* __restrict__ hits, uint64_t n, float denom, float* __restrict__ ao, uint32_t part,
+                              uint32_t num_parts, uint32_t block_samples) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  ao[i] = ex::sub(1.0f, ex::div((float)hits[i], denom));
+  const bool owned = num_parts <= 1 || (i / block_samples) % num_parts == part;
+  ao[i] = owned ? ex::sub(1.0f, ex::div((float)hits[i], denom)) : 0.0f;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -772,7 +772,8 @@ int aobake_set_samples(AoBake* ctx, const AoSamples* s, const size_t* per_instan
 
 size_t aobake_num_samples(const AoBake* ctx) { return ctx ? ctx->num_samples : 0; }
 
-int aobake_compute_ao_range(AoBake* ctx, size_t begin, size_t end, int rays_per_sample, float offset, float maxdist, float* host_ao) {
+static int compute_ao_impl(AoBake* ctx, size_t begin, size_t end, int rays_per_sample, float offset, float maxdist, float* host_ao,
+                           uint32_t part, uint32_t num_parts, uint32_t block_samples) {
   if (!ctx) return AOBAKE_ERR_INVALID_ARGUMENT;
   if (!ctx->have_scene) return ctx->fail(AOBAKE_ERR_STATE, "compute_ao before set_scene");
   if (begin > end || end > ctx->num_samples) return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "sample range [%zu,%zu) outside [0,%llu)", begin, end, (unsigned long long)ctx->num_samples);
@@ -783,9 +784,31 @@ int aobake_compute_ao_range(AoBake* ctx, size_t begin, size_t end, int rays_per_
   const int q = sqrt_rays(rays_per_sample);
   if (q < 1 || q > 255) return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "sqrt(rays_per_sample) must be in [1,255]");
   const uint64_t n = end - begin;
-  ctx->timings.rays_traced = n * (uint64_t)q * q;
+  // interleaved partition: which 32-sample blocks this call owns
+  const uint64_t n_global_blocks = (n + 31) / 32;
+  uint32_t sb_blocks = 1;
+  uint64_t n_local_blocks = n_global_blocks, owned_samples = n;
+  if (num_parts > 1) {
+    if (part >= num_parts) return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "part %u of %u", part, num_parts);
+    if (block_samples == 0) block_samples = 65536;
+    if (block_samples % 32) return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "block_samples must be a multiple of 32");
+    sb_blocks = block_samples / 32;
+    const uint64_t n_sb = (n_global_blocks + sb_blocks - 1) / sb_blocks;
+    const uint64_t owned_sb = n_sb / num_parts + ((n_sb % num_parts) > part ? 1 : 0);
+    n_local_blocks = owned_sb * sb_blocks;
+    owned_samples = 0;
+    for (uint64_t sb = part; sb < n_sb; sb += num_parts) {
+      const uint64_t s0 = sb * (uint64_t)block_samples, s1 = std::min<uint64_t>(n, s0 + block_samples);
+      owned_samples += s1 - s0;
+    }
+  }
+  ctx->timings.rays_traced = owned_samples * (uint64_t)q * q;
   ctx->timings.trace_ms = 0.f;
   if (n == 0) return AOBAKE_OK;
+  if (num_parts > 1) {
+    // everything this part does not own reads as zero, so that an all-reduce (sum) assembles ao[]
+    CK(cudaMemsetAsync(ctx->d_hits.p + begin, 0, n * sizeof(uint32_t), st));
+  }
   const bool stats = ctx->params.collect_stats != 0;
   SampleView S{ctx->d_pos.p, ctx->d_nrm.p, ctx->d_fnrm.p};
   const BvhView bvh = bvh_view(ctx);
@@ -795,7 +818,7 @@ int aobake_compute_ao_range(AoBake* ctx, size_t begin, size_t end, int rays_per_
   int launches = 0;
   // trace_kernel: 0 = auto (persistent, except for launches too small to amortise its work
   // distribution: < 32 M rays), 1 = simple, 2 = persistent
-  const bool use_simple = ctx->params.trace_kernel == 1 || (ctx->params.trace_kernel == 0 && n * (uint64_t)q2 < (32ull << 20));
+  const bool use_simple = num_parts == 1 && (ctx->params.trace_kernel == 1 || (ctx->params.trace_kernel == 0 && n * (uint64_t)q2 < (32ull << 20)));
   if (use_simple) {
     // simple variant: enough (sample block, strata chunk) items to fill the machine
     const uint64_t n_blocks = (n + 31) / 32;
@@ -814,8 +837,8 @@ int aobake_compute_ao_range(AoBake* ctx, size_t begin, size_t end, int rays_per_
   } else {
     // persistent variant: one resident wave of CTAs (a multiple of the SM count), dynamic work fetch
     if (n > 0xfffffff0ull) return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "more than 2^32 samples in one range");
-    using KernelT = void (*)(BvhView, SampleView, uint64_t, uint32_t, int, float, float, uint32_t, uint32_t, uint32_t*, unsigned long long*,
-                             unsigned long long*);
+    using KernelT = void (*)(BvhView, SampleView, uint64_t, uint32_t, int, float, float, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t,
+                             uint32_t, uint32_t*, unsigned long long*, unsigned long long*);
     KernelT kern = ctx->two_level ? (stats ? (KernelT)k_ao_persistent<true, true> : (KernelT)k_ao_persistent<false, true>)
                                   : (stats ? (KernelT)k_ao_persistent<true, false> : (KernelT)k_ao_persistent<false, false>);
     int per_sm = 0;
@@ -823,19 +846,19 @@ int aobake_compute_ao_range(AoBake* ctx, size_t begin, size_t end, int rays_per_
     if (per_sm < 1) per_sm = 1;
     const uint64_t resident_threads = (uint64_t)per_sm * ctx->sm_count * kAoBlock;
     uint32_t n_chunks = 1;
-    while (n * n_chunks < 8 * resident_threads && n_chunks * 2 <= q2) n_chunks *= 2;
+    while (owned_samples * n_chunks < 8 * resident_threads && n_chunks * 2 <= q2) n_chunks *= 2;
     unsigned grid = (unsigned)(per_sm * ctx->sm_count);
-    const uint64_t items = n * n_chunks;
+    const uint64_t items = std::max<uint64_t>(owned_samples, 1) * n_chunks;
     if ((uint64_t)grid * kAoBlock > items) grid = (unsigned)((items + kAoBlock - 1) / kAoBlock);
-    if (n_chunks > 1) CK(cudaMemsetAsync(ctx->d_hits.p + begin, 0, n * sizeof(uint32_t), st));
+    if (n_chunks > 1 && num_parts == 1) CK(cudaMemsetAsync(ctx->d_hits.p + begin, 0, n * sizeof(uint32_t), st));
     CK(cudaMemsetAsync(ctx->d_counter.p, 0, sizeof(unsigned long long), st));
     const uint32_t refill = ctx->params.refill_below > 0 ? (uint32_t)ctx->params.refill_below : 28u;
-    kern<<<grid, kAoBlock, 0, st>>>(bvh, S, (uint64_t)begin, (uint32_t)n, q, offset, maxdist, n_chunks, refill, ctx->d_hits.p + begin,
-                                    ctx->d_counter.p, ctx->d_stats.p);
+    kern<<<grid, kAoBlock, 0, st>>>(bvh, S, (uint64_t)begin, (uint32_t)n, q, offset, maxdist, n_chunks, refill, part, num_parts, sb_blocks,
+                                    (uint32_t)n_local_blocks, ctx->d_hits.p + begin, ctx->d_counter.p, ctx->d_stats.p);
     CKL();
     launches++;
   }
-  k_ao_finalize<<<grid_for(n, 256), 256, 0, st>>>(ctx->d_hits.p + begin, n, (float)(q * q), ctx->d_ao.p + begin);
+  k_ao_finalize<<<grid_for(n, 256), 256, 0, st>>>(ctx->d_hits.p + begin, n, (float)(q * q), ctx->d_ao.p + begin, part, num_parts, sb_blocks * 32u);
   CKL();
   launches++;
   ctx->timings.kernel_launches = launches;
@@ -852,6 +875,17 @@ int aobake_compute_ao_range(AoBake* ctx, size_t begin, size_t end, int rays_per_
   }
   ctx->have_ao = true;
   return AOBAKE_OK;
+}
+
+int aobake_compute_ao_range(AoBake* ctx, size_t begin, size_t end, int rays_per_sample, float offset, float maxdist, float* host_ao) {
+  return compute_ao_impl(ctx, begin, end, rays_per_sample, offset, maxdist, host_ao, 0, 1, 0);
+}
+
+int aobake_compute_ao_interleaved(AoBake* ctx, uint32_t part, uint32_t num_parts, uint32_t block_samples, int rays_per_sample, float offset,
+                                  float maxdist) {
+  if (!ctx) return AOBAKE_ERR_INVALID_ARGUMENT;
+  if (num_parts == 0) return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "num_parts must be >= 1");
+  return compute_ao_impl(ctx, 0, ctx->num_samples, rays_per_sample, offset, maxdist, nullptr, part, num_parts, block_samples);
 }
 
 int aobake_compute_ao(AoBake* ctx, int rays_per_sample, float offset, float maxdist, float* host_ao) {

@@ -17,6 +17,12 @@ def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
     return (rank * total) // world, ((rank + 1) * total) // world
 
 
+def owned_mask(total: int, part: int, num_parts: int, block_samples: int = 65536) -> np.ndarray:
+    """Samples traced by `part` under the interleaved partition (aobake_compute_ao_interleaved):
+    super-blocks of block_samples samples, dealt round-robin."""
+    return (np.arange(total, dtype=np.int64) // block_samples) % num_parts == part
+
+
 def gather_shards_(full, world: int, group=None):
     """In-place exchange: `full` is a 1-D tensor of all samples' AO in which this rank has
     filled its own shard_range; afterwards every rank holds every shard.  Ragged shards are
@@ -51,16 +57,29 @@ class DistributedBaker:
         self.bk, self.rank, self.world, self.device, self.group = baker, rank, world, device, group
 
     def compute_ao(self, rays_per_sample: int, scene_offset: float, scene_maxdistance: float, gather: bool = True,
-                   download: bool = False) -> Optional[np.ndarray]:
+                   download: bool = False, interleave: bool = True, block_samples: int = 65536) -> Optional[np.ndarray]:
+        """interleave=True (default): rank r traces the 64k-sample super-blocks with index % R == r
+        (even load on scenes whose regions differ in traversal cost) and the resident ao[] arrays
+        are summed in place with one all-reduce — every other rank contributes exact zeros, so the
+        result is bit-identical to a single-GPU bake.  interleave=False: contiguous ranges and one
+        broadcast per owner."""
+        import torch
+        import torch.distributed as dist
         total = self.bk.num_samples
-        b, e = shard_range(total, self.rank, self.world)
-        self.bk.compute_ao(rays_per_sample, scene_offset, scene_maxdistance, download=False, begin=b, end=e)
+        if interleave and self.world > 1:
+            self.bk.compute_ao_interleaved(self.rank, self.world, rays_per_sample, scene_offset, scene_maxdistance,
+                                           block_samples)
+        else:
+            b, e = shard_range(total, self.rank, self.world)
+            self.bk.compute_ao(rays_per_sample, scene_offset, scene_maxdistance, download=False, begin=b, end=e)
         if gather and self.world > 1:
             ptr, n = self.bk.ao_device_ptr()
-            full = device_tensor(ptr, n, self.device)      # the context's resident ao[] — gathered in place
+            full = device_tensor(ptr, n, self.device)      # the context's resident ao[] — exchanged in place
             self.bk.synchronize()
-            gather_shards_(full, self.world, self.group)
-            import torch
+            if interleave:
+                dist.all_reduce(full, op=dist.ReduceOp.SUM, group=self.group)
+            else:
+                gather_shards_(full, self.world, self.group)
             torch.cuda.synchronize(self.device)
         if download:
             import torch

@@ -24,7 +24,10 @@ def main():
             bk.set_scene(scene, blockers)
             total, per = bk.distribute_samples(2, 10007)
             bk.sample_instances(per, 2, download=False)
-            ao = DistributedBaker(bk, rank, world, local).compute_ao(64, off, maxd, gather=True, download=True)
+            ao_c = DistributedBaker(bk, rank, world, local).compute_ao(64, off, maxd, gather=True, download=True, interleave=False)
+            ao = DistributedBaker(bk, rank, world, local).compute_ao(64, off, maxd, gather=True, download=True, interleave=True,
+                                                                      block_samples=2048)
+            assert np.array_equal(ao.view(np.uint32), ao_c.view(np.uint32)), 'interleaved != contiguous sharding'
             v_area = bk.map_ao_to_vertices(api.FILTER_AREA_BASED)
         if rank == 0:
             with api.Baker(device=local) as ref:

@@ -313,3 +313,30 @@ def test_least_squares_with_unsampled_regions(api):
     assert np.abs(v_ls - o_ls).max() <= VERTEX_AO_TOL and np.abs(v_area - o_area).max() <= VERTEX_AO_TOL
     assert (v_area == 0).mean() > 0.3          # a large unsampled region exists
     assert iters < 500
+
+
+@pytest.mark.parametrize("name", ["sphere_ground", "instanced"])
+@pytest.mark.parametrize("parts,block", [(2, 64), (3, 2048), (8, 32)])
+def test_interleaved_parts_sum_to_full_bake(api, name, parts, block):
+    """Multi-GPU interleaved partition, exercised on one GPU: the parts' AO arrays (zeros outside a
+    part's super-blocks) sum exactly to the single-launch result."""
+    scene, blockers = SCENES[name]
+    off, maxd = scenes.default_distances(scene)
+    with api.Baker() as bk:
+        bk.set_scene(scene, blockers)
+        total, per = bk.distribute_samples(1, 10007)
+        bk.sample_instances(per, 1, download=False)
+        want = bk.compute_ao(64, off, maxd)
+        acc = np.zeros(total, dtype=np.float32)
+        owned = np.zeros(total, dtype=np.int32)
+        rays = 0
+        for p in range(parts):
+            bk.compute_ao_interleaved(p, parts, 64, off, maxd, block_samples=block)
+            part = bk.download_ao()
+            rays += bk.timings().rays_traced
+            idx = (np.arange(total) // block) % parts == p
+            assert np.all(part[~idx] == 0.0)
+            owned += idx
+            acc += part
+        assert rays == total * 64 and np.all(owned == 1)
+        assert np.array_equal(acc.view(np.uint32), want.view(np.uint32))

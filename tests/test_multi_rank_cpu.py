@@ -11,7 +11,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from optix_prime_baking_b200 import scenes
-from optix_prime_baking_b200.multi_gpu import gather_shards_, shard_range
+from optix_prime_baking_b200.multi_gpu import gather_shards_, owned_mask, shard_range
 
 
 def test_shard_ranges_partition():
@@ -47,6 +47,12 @@ def _worker(rank, world, port, out_dir):
     full[b:e] = torch.from_numpy(ao)
     gather_shards_(full, world)
     np.save(os.path.join(out_dir, f"ao_{rank}.npy"), full.numpy())
+    # interleaved partition: owned super-blocks carry AO, everything else exact zeros, one all-reduce
+    mask = owned_mask(total, rank, world, 64)
+    ao_full, _ = orc.compute_ao(sb, 16, off, maxd)        # stand-in for the per-part GPU launch
+    inter = torch.from_numpy(np.where(mask, ao_full, np.float32(0.0)).astype(np.float32))
+    dist.all_reduce(inter, op=dist.ReduceOp.SUM)
+    np.save(os.path.join(out_dir, f"ao_inter_{rank}.npy"), inter.numpy())
     dist.barrier()
     dist.destroy_process_group()
 
@@ -64,3 +70,11 @@ def test_two_rank_gather_matches_single_rank(tmp_path):
     for r in range(world):
         got = np.load(tmp_path / f"ao_{r}.npy")
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+        got = np.load(tmp_path / f"ao_inter_{r}.npy")
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_owned_masks_partition():
+    for total, parts, block in [(10007, 3, 64), (1, 2, 32), (200000, 8, 65536), (131072, 2, 65536)]:
+        cover = sum(owned_mask(total, p, parts, block).astype(np.int32) for p in range(parts))
+        assert np.all(cover == 1)
