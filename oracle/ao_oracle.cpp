@@ -337,10 +337,13 @@ inline bool box_hit(const Box& b, const Ray& r, V3 id) {
   float tn = r.tmin, tf = r.tmax;
   const float o[3] = {r.o.x, r.o.y, r.o.z}, iv[3] = {id.x, id.y, id.z};
   for (int k = 0; k < 3; k++) {
-    float t0 = (b.lo[k] - o[k]) * iv[k], t1 = (b.hi[k] - o[k]) * iv[k];
-    float a = std::fmin(t0, t1), c = std::fmax(t0, t1);  // NaN-dropping
-    tn = std::fmax(tn, a);
-    tf = std::fmin(tf, c);
+    const float t0 = (b.lo[k] - o[k]) * iv[k], t1 = (b.hi[k] - o[k]) * iv[k];
+    // 0 * inf: the origin sits exactly on a slab plane of an exactly-zero direction component —
+    // it is inside this slab (conservative), no constraint
+    if (t0 != t0 || t1 != t1) continue;
+    const float a = t0 < t1 ? t0 : t1, c = t0 < t1 ? t1 : t0;
+    if (a > tn) tn = a;
+    if (c < tf) tf = c;
   }
   return tn <= tf * 1.0000005f;
 }
