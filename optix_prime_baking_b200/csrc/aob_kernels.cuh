@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(256) k_ao_simple(BvhView bvh, SampleView S, ui
 //     columns) for the first kSmStack entries and spills to local memory beyond;
 //   * the Woop shear constants are computed lazily, only by lanes that reach a triangle.
 constexpr int kAoBlock = 128;
-constexpr int kSmStack = 12;
+constexpr int kSmStack = 6;
 
 template <bool STATS, bool TWO_LEVEL>
 __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleView S, uint64_t begin, uint32_t n, int q, float offset,
