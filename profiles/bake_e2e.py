@@ -61,6 +61,24 @@ for rep in range(2):
            "vertex_ao_mean": float(np.mean([x.mean() for x in v])), "vertex_ao_min": float(min(x.min() for x in v)),
            "vertex_ao_max": float(max(x.max() for x in v))}
     out[f"run{rep}"] = res
+if rank == 0 and "--oracle" in sys.argv:
+    # the same bake on the CPU oracle (host cores), phase by phase — BASELINE.md §2
+    from tests.oracle_binding import Oracle, lib
+    orc = Oracle(scene, blockers)
+    t0 = time.perf_counter()
+    ototal, oper = orc.distribute_samples(min_per, requested)
+    osb = orc.sample_instances(oper, min_per)
+    t1 = time.perf_counter()
+    _ = orc.tracer
+    t2 = time.perf_counter()
+    oao, _h = orc.compute_ao(osb, rays, off, maxd)
+    t3 = time.perf_counter()
+    ov = orc.filter_least_squares(osb, oao, 0.1, tol=1e-6) if mode == "ls" else orc.filter_area(osb, oao)
+    t4 = time.perf_counter()
+    q = int(round(rays ** 0.5))
+    out["oracle_cpu"] = {"cores": int(lib().ao_oracle_num_threads()), "sample_s": t1 - t0, "bvh_build_s": t2 - t1, "trace_s": t3 - t2,
+                         "trace_Mrays_per_s": ototal * q * q / (t3 - t2) / 1e6, "vertex_map_s": t4 - t3, "bake_seconds": t4 - t0,
+                         "max_abs_vertex_ao_diff_vs_gpu": float(max(np.abs(a - b).max() for a, b in zip(ov, v)))}
 if rank == 0:
     print(json.dumps(out))
 if world > 1:
