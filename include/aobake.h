@@ -141,7 +141,7 @@ typedef struct AoStats {
   uint64_t instance_entries;
   uint64_t rays;
   int32_t two_level;
-  int32_t reserved[7];
+  int32_t reserved[7];            /* [0] = depth of the top-level 8-wide tree, [1] = deepest BLAS (two-level) */
 } AoStats;
 
 typedef struct AoBake AoBake;

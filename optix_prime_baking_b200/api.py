@@ -65,7 +65,7 @@ def load_library(path: Optional[str] = None):
     global _LIB
     if _LIB is not None and path is None:
         return _LIB
-    p = path or _LIB_PATH
+    p = path or os.environ.get("AOBAKE_LIB") or _LIB_PATH   # AOBAKE_LIB: A/B-test another build of the same ABI
     if not os.path.exists(p):
         raise RuntimeError(f"{p} is missing: build it with `python -m optix_prime_baking_b200.build` "
                            "(requires nvcc; there is no CPU fallback)")

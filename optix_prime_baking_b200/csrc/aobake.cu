@@ -161,6 +161,7 @@ namespace {
 struct Segment {
   uint32_t root = 0;
   uint32_t node_count = 0;
+  int levels = 1;  // depth of the 8-wide tree (collapse rounds) — bounds the traversal stack
   float box[6] = {0, 0, 0, 0, 0, 0};
 };
 
@@ -232,6 +233,7 @@ int build_segment(AoBake* ctx, const F4* d_plo, const F4* d_phi, uint32_t n, uin
   }
   if (hc[1] != n) return ctx->fail(AOBAKE_ERR_CUDA, "BVH collapse emitted %u of %u primitives", hc[1], n);
   out->node_count = hc[0];
+  out->levels = levels;
   CK(cudaMemcpyAsync(out->box, d_box.p, sizeof(out->box), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return AOBAKE_OK;
@@ -513,6 +515,10 @@ int aobake_set_scene(AoBake* ctx, const AoScene* scene, const AoScene* blockers)
     CKL();
     Segment seg;
     if ((rc = build_segment(ctx, plo.p, phi.p, n, 3, 0, 0, nodes.p, leaf_prims.p, &seg))) return rc;
+    // every visited node pushes at most one stack entry: the stack never holds more than the tree depth
+    if (seg.levels + 2 > kStackSize)
+      return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "BVH depth %d exceeds the traversal stack (%d entries)", seg.levels, kStackSize);
+    ctx->stats.reserved[0] = seg.levels;
     CK(ctx->d_tris.alloc(3ull * std::max(n, 1u)));
     if (n) k_gather_tris<<<grid_for(n, 256), 256, 0, st>>>(soup.p, leaf_prims.p, n, 0, ctx->d_tris.p);
     CKL();
@@ -618,6 +624,15 @@ int aobake_set_scene(AoBake* ctx, const AoScene* scene, const AoScene* blockers)
     CK(ctx->d_insts.alloc(recs.size()));
     CK(cudaMemcpyAsync(ctx->d_insts.p, recs.data(), recs.size() * sizeof(F4), cudaMemcpyHostToDevice, st));
     CK(cudaStreamSynchronize(st));
+    {
+      int blas_levels = 0;
+      for (const Segment& sg : segs) blas_levels = std::max(blas_levels, sg.levels);
+      // TLAS entries (node group + primitive group per level) + sentinel + BLAS entries
+      if (2 * tl.levels + blas_levels + 3 > kStackSize)
+        return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "TLAS depth %d + BLAS depth %d exceed the traversal stack (%d entries)", tl.levels, blas_levels, kStackSize);
+      ctx->stats.reserved[0] = tl.levels;
+      ctx->stats.reserved[1] = blas_levels;
+    }
     const uint32_t total_nodes = node_off + tl.node_count;
     CK(ctx->d_nodes.alloc(total_nodes));
     CK(cudaMemcpyAsync(ctx->d_nodes.p, nodes.p, total_nodes * sizeof(Node8), cudaMemcpyDeviceToDevice, st));

@@ -26,4 +26,4 @@ with api.Baker(trace_kernel=tk) as bk:
         t = bk.timings()
         print(f"{w} kernel {tk} samples {n} rays {t.rays_traced} trace_ms {t.trace_ms:.3f} Grays/s {t.rays_traced / t.trace_ms / 1e6:.3f}", flush=True)
     st = bk.stats()
-    print(f"bvh nodes {st.num_bvh_nodes} tris {st.num_bvh_triangles} bytes {st.bvh_bytes} build_ms {bk.timings().bvh_build_ms:.2f}")
+    print(f"bvh nodes {st.num_bvh_nodes} tris {st.num_bvh_triangles} bytes {st.bvh_bytes} build_ms {bk.timings().bvh_build_ms:.2f} depth {st.reserved[0]} blas_depth {st.reserved[1]}")
