@@ -400,6 +400,11 @@ AOB_D uint32_t shift_in_sign(uint32_t acc, uint32_t lo) {
 // constant o and of the final FMA is bounded by 5e-7*|b| + 0.008*|ad|; near/far are pushed
 // apart by pad = 1e-6*|b| + 0.0234*|ad| (2.3 % of one quantisation step), so a box the exact
 // ray touches is never culled and no per-child padding multiply is needed.
+// CLAMP_TMAX = false drops the far clamp of the slab interval (8 FMNMX per node on the binding ALU
+// pipe): legal whenever tmax exceeds the scene diagonal, which is the AO default (10 x the scene
+// extent) — culling by tmax can then never reject a box inside the scene, and the triangle test
+// still enforces t < tmax exactly.
+template <bool CLAMP_TMAX = true>
 AOB_D uint32_t intersect_node8(const U4* nodes, uint32_t idx, const RayState& r, const NodeConsts& nc, uint32_t* child_base,
                                uint32_t* prim_base, uint32_t* imask) {
   const U4* p = nodes + 5ull * idx;
@@ -437,7 +442,7 @@ AOB_D uint32_t intersect_node8(const U4* nodes, uint32_t idx, const RayState& r,
       const float tny = fmaf(q2f(nwy, k, nc), ady, ony), tfy = fmaf(q2f(fwy, k, nc), ady, ofy);
       const float tnz = fmaf(q2f(nwz, k, nc), adz, onz), tfz = fmaf(q2f(fwz, k, nc), adz, ofz);
       const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, r.tmin));
-      const float tf = fminf(fminf(tfx, tfy), fminf(tfz, r.tmax));
+      const float tf = CLAMP_TMAX ? fminf(fminf(tfx, tfy), fminf(tfz, r.tmax)) : fminf(fminf(tfx, tfy), tfz);
       miss = shift_in_sign(miss, as_uint(tf - tn));
     }
   }

@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(256) k_ao_simple(BvhView bvh, SampleView S, ui
 constexpr int kAoBlock = 128;
 constexpr int kSmStack = 6;
 
-template <bool STATS, bool TWO_LEVEL>
+template <bool STATS, bool TWO_LEVEL, bool CLAMP_TMAX>
 __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleView S, uint64_t begin, uint32_t n, int q, float offset,
                                                              float maxdist, uint32_t n_chunks, uint32_t refill_below,
                                                              uint32_t part, uint32_t num_parts, uint32_t sb_blocks, uint32_t n_local_blocks,
@@ -550,7 +550,7 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
           const uint32_t node = G.x + (uint32_t)__popc(G.y & 0xffu & ((1u << slot) - 1u));
           if (G.y & 0xff000000u) push(sp, G);
           uint32_t cb, pb, im;
-          const uint32_t hm = intersect_node8(bvh.nodes, node, r, nc, &cb, &pb, &im);
+          const uint32_t hm = intersect_node8<CLAMP_TMAX>(bvh.nodes, node, r, nc, &cb, &pb, &im);
           if (STATS) c_nodes++;
           G.x = cb; G.y = (hm & 0xff000000u) | im;
           T.x = pb; T.y = hm & 0x00ffffffu;

@@ -174,11 +174,16 @@ AOB_HD V3 cosine_dir(float u0, float u1, V3 n, const Onb& o) {
 }
 // direction of stratum `pass` (= px*q+py) of global sample g.
 AOB_HD V3 ao_ray_dir(uint32_t g, uint32_t pass, int q, V3 n, V3 fn, const Onb& onb) {
-  const uint32_t px = pass / (uint32_t)q, py = pass - px * (uint32_t)q;
-  uint32_t seed = tea<2>((pass << 16) | pass, g);
   // (p + rnd) / q: for power-of-two q (all BASELINE configs) the reciprocal is exact and the
   // multiply is bit-identical to the IEEE division; other q take the division.
   const bool pow2 = (q & (q - 1)) == 0;
+#if defined(__CUDA_ARCH__)
+  const uint32_t px = pow2 ? pass >> (__ffs(q) - 1) : pass / (uint32_t)q;  // no runtime integer division on the common path
+#else
+  const uint32_t px = pass / (uint32_t)q;
+#endif
+  const uint32_t py = pass - px * (uint32_t)q;
+  uint32_t seed = tea<2>((pass << 16) | pass, g);
   const float fq = (float)q, rq = ex::div(1.0f, fq);
   const float s0 = ex::add((float)px, rnd(seed)), s1 = ex::add((float)py, rnd(seed));
   float u0 = pow2 ? ex::mul(s0, rq) : ex::div(s0, fq);

@@ -122,6 +122,7 @@ struct AoBake {
   DBuf<F4> d_insts;
   uint32_t root = 0;
   bool two_level = false;
+  float scene_diag = 0.f;   // diagonal of the world box of everything in the BVH
   AoStats stats{};
 
   // samples + AO
@@ -527,6 +528,8 @@ int aobake_set_scene(AoBake* ctx, const AoScene* scene, const AoScene* blockers)
     CK(cudaStreamSynchronize(st));
     ctx->d_insts.release();
     ctx->root = 0;
+    ctx->scene_diag = n ? sqrtf((seg.box[3] - seg.box[0]) * (seg.box[3] - seg.box[0]) + (seg.box[4] - seg.box[1]) * (seg.box[4] - seg.box[1]) +
+                                (seg.box[5] - seg.box[2]) * (seg.box[5] - seg.box[2])) : 0.f;
     ctx->stats.num_bvh_nodes = seg.node_count;
     ctx->stats.num_bvh_triangles = n;
   } else {
@@ -638,6 +641,8 @@ int aobake_set_scene(AoBake* ctx, const AoScene* scene, const AoScene* blockers)
     CK(cudaMemcpyAsync(ctx->d_nodes.p, nodes.p, total_nodes * sizeof(Node8), cudaMemcpyDeviceToDevice, st));
     CK(cudaStreamSynchronize(st));
     ctx->root = tl.root;
+    ctx->scene_diag = nI ? sqrtf((tl.box[3] - tl.box[0]) * (tl.box[3] - tl.box[0]) + (tl.box[4] - tl.box[1]) * (tl.box[4] - tl.box[1]) +
+                                 (tl.box[5] - tl.box[2]) * (tl.box[5] - tl.box[2])) : 0.f;
     ctx->stats.num_bvh_nodes = total_nodes;
     ctx->stats.num_bvh_triangles = tri_total;
     ctx->stats.num_tlas_instances = nI;
@@ -854,8 +859,15 @@ static int compute_ao_impl(AoBake* ctx, size_t begin, size_t end, int rays_per_s
     if (n > 0xfffffff0ull) return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "more than 2^32 samples in one range");
     using KernelT = void (*)(BvhView, SampleView, uint64_t, uint32_t, int, float, float, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t,
                              uint32_t, uint32_t*, unsigned long long*, unsigned long long*);
-    KernelT kern = ctx->two_level ? (stats ? (KernelT)k_ao_persistent<true, true> : (KernelT)k_ao_persistent<false, true>)
-                                  : (stats ? (KernelT)k_ao_persistent<true, false> : (KernelT)k_ao_persistent<false, false>);
+    // the far clamp of the node test is only needed when maxdist can actually cull inside the scene
+    const bool clamp = !(maxdist > 1.01f * ctx->scene_diag + fabsf(offset));
+    KernelT kern;
+    if (clamp)
+      kern = ctx->two_level ? (stats ? (KernelT)k_ao_persistent<true, true, true> : (KernelT)k_ao_persistent<false, true, true>)
+                            : (stats ? (KernelT)k_ao_persistent<true, false, true> : (KernelT)k_ao_persistent<false, false, true>);
+    else
+      kern = ctx->two_level ? (stats ? (KernelT)k_ao_persistent<true, true, false> : (KernelT)k_ao_persistent<false, true, false>)
+                            : (stats ? (KernelT)k_ao_persistent<true, false, false> : (KernelT)k_ao_persistent<false, false, false>);
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kAoBlock, 0));
     if (per_sm < 1) per_sm = 1;
