@@ -351,7 +351,7 @@ def main():
     nodes_per_ray = s3.node_visits / max(s3.rays, 1)
     tris_per_ray = s3.triangle_tests / max(s3.rays, 1)
     insts_per_ray = s3.instance_entries / max(s3.rays, 1)
-    bytes_per_ray = 80.0 * nodes_per_ray + 48.0 * tris_per_ray + 64.0 * insts_per_ray + 40.0 / (q * q)
+    bytes_per_ray = 80.0 * nodes_per_ray + 48.0 * tris_per_ray + 80.0 * insts_per_ray + 40.0 / (q * q)
     kms = float(np.mean(kernel_ms))
     achieved = rays_rank * bytes_per_ray / (kms * 1e-3) / 1e9
     peak, peak_src = peaks()
@@ -385,7 +385,7 @@ def main():
                          "traffic": traffic, "peak_source": peak_src, "kernel": "k_ao (fused raygen+traverse+accumulate)",
                          "kernel_ms": kms, "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray,
                          "tris_per_ray": tris_per_ray, "instances_per_ray": insts_per_ray,
-                         "note": "algorithmic bytes = 80 B/node visit + 48 B/triangle test + 64 B/instance entry + 40 B/sample "
+                         "note": "algorithmic bytes = 80 B/node visit + 48 B/triangle test + 80 B/instance entry + 40 B/sample "
                                  "(SURVEY §8d); traversal is latency/L2 bound, see DESIGN.md"},
             "cpu_baseline": cpu,
         }

@@ -9,7 +9,8 @@
 //           scale per axis, an internal-child mask, and a meta byte per slot.
 //   tris  : 48-byte records = 3 x float4 (v0, v1, v2; w lanes carry the source primitive id),
 //           in leaf order, so a leaf is (prim_base + offset, count <= 3).
-//   insts : 64-byte records = 3 x float4 rows of the world->object 3x4 + uint4{blas_root,..}.
+//   insts : 80-byte records = 3 x float4 rows of the world->object 3x4 + uint4{blas_root, id, -, -}
+//           + float4 world-space bounding sphere (centre, radius^2) for the pre-test.
 //
 // Kernel bodies are written as `*_body(tid, ...)` functions that also compile under plain
 // g++ (AOB_HOST_EMU) — tests/emu runs the identical code serially on the CPU.
@@ -73,11 +74,12 @@ static_assert(sizeof(Node8) == 80, "Node8 must be 80 bytes");
 constexpr uint32_t kLeafBit = 0x80000000u;
 constexpr uint32_t kSentinel = 0xFFFFFFFFu;
 constexpr int kStackSize = 48;
+constexpr int kInstF4 = 5;  // float4s per instance record
 
 struct BvhView {
   const U4* nodes;   // 5 x U4 per node
   const F4* tris;    // 3 x F4 per triangle
-  const F4* insts;   // 4 x F4 per instance (two-level only)
+  const F4* insts;   // kInstF4 x F4 per instance (two-level only)
   uint32_t root;     // node index where traversal starts (TLAS root when two_level)
   uint32_t two_level;
 };
@@ -507,6 +509,20 @@ AOB_D bool test_tri_group(const F4* tris, uint32_t base, uint32_t mask, V3 org, 
   }
 }
 
+// Conservative world-space pre-test of an instance: can the ray touch its bounding sphere
+// (centre s.xyz, padded radius^2 s.w) at all?  ~20 instructions against the ~100 of the exact ray
+// transform plus the BLAS root test it avoids; for compact meshes the sphere is far tighter than
+// the world AABB in the TLAS (a ball fills 52 % of its bounding cube).
+AOB_D bool sphere_may_hit(V3 o, V3 d, F4 s) {
+  const float ocx = s.x - o.x, ocy = s.y - o.y, ocz = s.z - o.z;
+  const float c = ocx * ocx + ocy * ocy + ocz * ocz - s.w;
+  if (c <= 0.0f) return true;                 // origin inside the sphere
+  const float b = ocx * d.x + ocy * d.y + ocz * d.z;
+  if (b <= 0.0f) return false;                // sphere entirely behind the origin
+  const float dd = d.x * d.x + d.y * d.y + d.z * d.z;
+  return b * b * 1.00001f >= dd * c;          // discriminant >= 0, with slack for rounding
+}
+
 // Any-hit traversal of one ray with a caller-provided stack of kStackSize entries.
 template <bool STATS>
 AOB_D bool trace_any_hit(const BvhView& bvh, V3 org, V3 dir, float tmin, float tmax, U2* stack, TraceCounters* cnt) {
@@ -546,14 +562,15 @@ AOB_D bool trace_any_hit(const BvhView& bvh, V3 org, V3 dir, float tmin, float t
       const int b = ffs32(T.y) - 1;
       T.y &= T.y - 1u;
       const uint32_t prim = T.x + (uint32_t)b;
+      if (!sphere_may_hit(org, dir, ld_f4(bvh.insts + (uint64_t)kInstF4 * prim + 4))) continue;
       {
         // instance leaf: save the TLAS continuation, switch to object space
         if (T.y) stack[sp++] = T;
         if (G.y & 0xff000000u) stack[sp++] = G;
         U2 s; s.x = kSentinel; s.y = 0;
         stack[sp++] = s;
-        const F4 r0 = ld_f4(bvh.insts + 4ull * prim), r1 = ld_f4(bvh.insts + 4ull * prim + 1), r2 = ld_f4(bvh.insts + 4ull * prim + 2);
-        const F4 r3 = ld_f4(bvh.insts + 4ull * prim + 3);
+        const F4* rec = bvh.insts + (uint64_t)kInstF4 * prim;
+        const F4 r0 = ld_f4(rec), r1 = ld_f4(rec + 1), r2 = ld_f4(rec + 2), r3 = ld_f4(rec + 3);
         const float m[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
         if (STATS) cnt->insts++;
         ray_setup(r, xf_point(m, org), xf_vector(m, dir), tmin, tmax);

@@ -125,6 +125,18 @@ __global__ void k_instance_bounds(const float* __restrict__ verts, uint32_t nV, 
     }
   }
 }
+// max squared distance of an instance's transformed vertices from `centre` (non-negative floats
+// order like their bit patterns, so atomicMax on the bits works)
+__global__ void k_instance_radius2(const float* __restrict__ verts, uint32_t nV, Xf12 xf, float cx, float cy, float cz, uint32_t* r2bits) {
+  float m = 0.0f;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nV; i += gridDim.x * blockDim.x) {
+    const V3 w = xf_point(xf.m, v3(verts[3ull * i], verts[3ull * i + 1], verts[3ull * i + 2]));
+    const float dx = w.x - cx, dy = w.y - cy, dz = w.z - cz;
+    m = fmaxf(m, dx * dx + dy * dy + dz * dz);
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(r2bits, __float_as_uint(m));
+}
 __global__ void k_decode_bounds_n(const int* f6, float* out6, uint32_t n) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out6[i] = ordered_to_float(f6[i]);
@@ -565,25 +577,29 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
             hit = test_tri_group(bvh.tris, T.x, T.y, r.org, r.dir, 0.0f, maxdist, &tested);
             if (STATS) c_tris += tested;
           } else if (TWO_LEVEL) {
-            // first instance of the group: save the TLAS continuation, switch to object space
-            const int b = __ffs((int)T.y) - 1;
-            T.y &= T.y - 1u;
-            const uint64_t prim = (uint64_t)T.x + (uint32_t)b;
-            if (T.y) push(sp, T);
-            if (G.y & 0xff000000u) push(sp, G);
-            U2 sen;
-            sen.x = kSentinel; sen.y = 0;
-            push(sp, sen);
-            const F4 r0 = ld_f4(bvh.insts + 4 * prim), r1 = ld_f4(bvh.insts + 4 * prim + 1), r2 = ld_f4(bvh.insts + 4 * prim + 2);
-            const F4 r3 = ld_f4(bvh.insts + 4 * prim + 3);
-            const float m[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
-            if (STATS) c_insts++;
-            r.org = xf_point(m, org);
-            r.dir = xf_vector(m, wdir);
-            r.idir = v3(safe_rcp(r.dir.x), safe_rcp(r.dir.y), safe_rcp(r.dir.z));
-            in_blas = true;
-            G.x = __float_as_uint(r3.x);
-            G.y = (1u << 24) | 1u;
+            // instances of the group: skip those whose bounding sphere the world ray cannot touch,
+            // enter the first one it can — save the TLAS continuation, switch to object space
+            while (T.y) {
+              const int b = __ffs((int)T.y) - 1;
+              T.y &= T.y - 1u;
+              const F4* rec = bvh.insts + (uint64_t)kInstF4 * ((uint64_t)T.x + (uint32_t)b);
+              if (!sphere_may_hit(org, wdir, ld_f4(rec + 4))) continue;
+              if (T.y) push(sp, T);
+              if (G.y & 0xff000000u) push(sp, G);
+              U2 sen;
+              sen.x = kSentinel; sen.y = 0;
+              push(sp, sen);
+              const F4 r0 = ld_f4(rec), r1 = ld_f4(rec + 1), r2 = ld_f4(rec + 2), r3 = ld_f4(rec + 3);
+              const float m[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
+              if (STATS) c_insts++;
+              r.org = xf_point(m, org);
+              r.dir = xf_vector(m, wdir);
+              r.idir = v3(safe_rcp(r.dir.x), safe_rcp(r.dir.y), safe_rcp(r.dir.z));
+              in_blas = true;
+              G.x = __float_as_uint(r3.x);
+              G.y = (1u << 24) | 1u;
+              break;
+            }
           }
         }
         // Ray end and restart are written once, straight-line: lanes ending on a hit, lanes ending

@@ -568,6 +568,7 @@ int aobake_set_scene(AoBake* ctx, const AoScene* scene, const AoScene* blockers)
     const uint32_t nI = (uint32_t)all.size();
     std::vector<F4> hlo(std::max(nI, 1u)), hhi(std::max(nI, 1u));
     std::vector<uint32_t> inst_blas(nI);
+    std::vector<float> inst_r2, inst_center;
     {
       DBuf<int> d_ib;
       DBuf<float> d_fb;
@@ -586,6 +587,26 @@ int aobake_set_scene(AoBake* ctx, const AoScene* scene, const AoScene* blockers)
       std::vector<float> hb(6ull * std::max(nI, 1u));
       if (nI) CK(cudaMemcpyAsync(hb.data(), d_fb.p, 6ull * nI * sizeof(float), cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
+      // bounding sphere about the centre of the world box: max vertex distance (second pass)
+      DBuf<uint32_t> d_r2;
+      CK(d_r2.alloc(std::max(nI, 1u)));
+      CK(cudaMemsetAsync(d_r2.p, 0, std::max(nI, 1u) * sizeof(uint32_t), st));
+      for (uint32_t i = 0; i < nI; i++) {
+        const DeviceMesh* m = all[i].mesh;
+        if (!m->nV) continue;
+        Xf12 xf;
+        memcpy(xf.m, all[i].inst->xf, sizeof(xf.m));
+        const float* b = &hb[6ull * i];
+        k_instance_radius2<<<std::min<unsigned>(grid_for(m->nV, 256), 64u), 256, 0, st>>>(m->verts.p, (uint32_t)m->nV, xf, 0.5f * (b[0] + b[3]),
+                                                                                         0.5f * (b[1] + b[4]), 0.5f * (b[2] + b[5]), d_r2.p + i);
+      }
+      CKL();
+      inst_r2.assign(std::max(nI, 1u), 0.f);
+      if (nI) CK(cudaMemcpyAsync(inst_r2.data(), d_r2.p, nI * sizeof(float), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      inst_center.assign(3ull * std::max(nI, 1u), 0.f);
+      for (uint32_t i = 0; i < nI; i++)
+        for (int k = 0; k < 3; k++) inst_center[3ull * i + k] = 0.5f * (hb[6ull * i + k] + hb[6ull * i + 3 + k]);
       for (uint32_t i = 0; i < nI; i++) {
         const bool is_blocker = i >= ctx->insts.size();
         const uint32_t mi = all[i].inst->mesh + (is_blocker ? (uint32_t)ctx->meshes.size() : 0u);
@@ -615,14 +636,19 @@ int aobake_set_scene(AoBake* ctx, const AoScene* scene, const AoScene* blockers)
     std::vector<uint32_t> order(nI);
     if (nI) CK(cudaMemcpyAsync(order.data(), leaf_insts.p, nI * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    std::vector<F4> recs(4ull * std::max(nI, 1u));
+    std::vector<F4> recs((size_t)kInstF4 * std::max(nI, 1u));
     for (uint32_t k = 0; k < nI; k++) {
       const HostInstance* I = all[order[k]].inst;
-      for (int r = 0; r < 3; r++) { F4 f; f.x = I->inv[4 * r]; f.y = I->inv[4 * r + 1]; f.z = I->inv[4 * r + 2]; f.w = I->inv[4 * r + 3]; recs[4ull * k + r] = f; }
+      for (int r = 0; r < 3; r++) { F4 f; f.x = I->inv[4 * r]; f.y = I->inv[4 * r + 1]; f.z = I->inv[4 * r + 2]; f.w = I->inv[4 * r + 3]; recs[(size_t)kInstF4 * k + r] = f; }
       F4 f;
       uint32_t rootidx = segs[inst_blas[order[k]]].root, id = order[k];
       memcpy(&f.x, &rootidx, 4); memcpy(&f.y, &id, 4); f.z = 0.f; f.w = 0.f;
-      recs[4ull * k + 3] = f;
+      recs[(size_t)kInstF4 * k + 3] = f;
+      // bounding sphere, radius^2 padded against the rounding of the test and of the transforms
+      F4 sph;
+      sph.x = inst_center[3ull * order[k]]; sph.y = inst_center[3ull * order[k] + 1]; sph.z = inst_center[3ull * order[k] + 2];
+      sph.w = inst_r2[order[k]] * 1.0002f + 1e-30f;
+      recs[(size_t)kInstF4 * k + 4] = sph;
     }
     CK(ctx->d_insts.alloc(recs.size()));
     CK(cudaMemcpyAsync(ctx->d_insts.p, recs.data(), recs.size() * sizeof(F4), cudaMemcpyHostToDevice, st));
@@ -647,7 +673,7 @@ int aobake_set_scene(AoBake* ctx, const AoScene* scene, const AoScene* blockers)
     ctx->stats.num_bvh_triangles = tri_total;
     ctx->stats.num_tlas_instances = nI;
   }
-  ctx->stats.bvh_bytes = ctx->stats.num_bvh_nodes * sizeof(Node8) + ctx->stats.num_bvh_triangles * 48 + ctx->stats.num_tlas_instances * 64;
+  ctx->stats.bvh_bytes = ctx->stats.num_bvh_nodes * sizeof(Node8) + ctx->stats.num_bvh_triangles * 48 + ctx->stats.num_tlas_instances * 16 * kInstF4;
   CK(cudaEventRecord(ctx->ev1, st));
   CK(cudaStreamSynchronize(st));
   CK(cudaEventElapsedTime(&ctx->timings.bvh_build_ms, ctx->ev0, ctx->ev1));

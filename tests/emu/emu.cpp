@@ -152,6 +152,25 @@ void* emu_bvh_create_two_level(uint32_t num_meshes, const float* const* mesh_tri
     for (int r = 0; r < 3; r++) { F4 f; f.x = inv[4 * r]; f.y = inv[4 * r + 1]; f.z = inv[4 * r + 2]; f.w = inv[4 * r + 3]; B->insts.push_back(f); }
     F4 f; f.x = as_float(roots[inst_mesh[id]]); f.y = as_float(id); f.z = 0; f.w = 0;
     B->insts.push_back(f);
+    // bounding sphere about the centre of the (unpadded) world box of the transformed vertices
+    {
+      const float* xf = inst_xform16 + 16 * (size_t)id;
+      const float* v9 = mesh_tris9[inst_mesh[id]];
+      const uint32_t nv = 3 * mesh_ntris[inst_mesh[id]];
+      V3 lo = v3(1e30f, 1e30f, 1e30f), hi = v3(-1e30f, -1e30f, -1e30f);
+      for (uint32_t q = 0; q < nv; q++) {
+        V3 w = xf_point(xf, v3(v9[3 * q], v9[3 * q + 1], v9[3 * q + 2]));
+        lo = v3(fminf(lo.x, w.x), fminf(lo.y, w.y), fminf(lo.z, w.z)); hi = v3(fmaxf(hi.x, w.x), fmaxf(hi.y, w.y), fmaxf(hi.z, w.z));
+      }
+      F4 s; s.x = 0.5f * (lo.x + hi.x); s.y = 0.5f * (lo.y + hi.y); s.z = 0.5f * (lo.z + hi.z);
+      float r2 = 0.f;
+      for (uint32_t q = 0; q < nv; q++) {
+        V3 w = xf_point(xf, v3(v9[3 * q], v9[3 * q + 1], v9[3 * q + 2]));
+        r2 = fmaxf(r2, (w.x - s.x) * (w.x - s.x) + (w.y - s.y) * (w.y - s.y) + (w.z - s.z) * (w.z - s.z));
+      }
+      s.w = r2 * 1.0002f + 1e-30f;
+      B->insts.push_back(s);
+    }
   }
   return B;
 }
