@@ -675,19 +675,6 @@ __global__ void k_area_final(const double* __restrict__ num, const double* __res
 }
 
 // ---- least squares (bake_filter_least_squares.cpp; Kavan et al. 2011) ---------------------
-// sampled mass blocks per triangle (6 unique entries) and rhs
-__global__ void k_ls_mass(const AoSampleInfo* __restrict__ info, const float* __restrict__ ao, uint64_t begin, uint64_t count,
-                          const uint32_t* __restrict__ tris, double* __restrict__ Mt, double* __restrict__ rhs) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
-  const AoSampleInfo si = info[begin + i];
-  const double dA = si.dA, a = ao[begin + i], b0 = si.bary[0], b1 = si.bary[1], b2 = si.bary[2];
-  double* M = Mt + 6ull * si.tri_idx;
-  atomicAdd(&M[0], dA * b0 * b0); atomicAdd(&M[1], dA * b0 * b1); atomicAdd(&M[2], dA * b0 * b2);
-  atomicAdd(&M[3], dA * b1 * b1); atomicAdd(&M[4], dA * b1 * b2); atomicAdd(&M[5], dA * b2 * b2);
-  const uint32_t* idx = tris + 3ull * si.tri_idx;
-  atomicAdd(&rhs[idx[0]], dA * a * b0); atomicAdd(&rhs[idx[1]], dA * a * b1); atomicAdd(&rhs[idx[2]], dA * a * b2);
-}
 // half-edge keys: (min(a,b) << 32 | max(a,b)), value = 3*tri + e; degenerate edges get key ~0
 __global__ void k_ls_halfedges(const uint32_t* __restrict__ tris, uint64_t nT, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -702,45 +689,108 @@ struct LsEdge {
   uint32_t i, j, p, q;
   double c[4];
 };
-// one thread per sorted half-edge; the first of a run of >= 2 equal keys emits an interior edge
-__global__ void k_ls_edges(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t nH,
-                           const uint32_t* __restrict__ tris, const float* __restrict__ verts, Xf12 xf,
-                           LsEdge* __restrict__ edges, uint32_t* __restrict__ edge_count) {
+// ---- batched (block-diagonal over instances) least-squares assembly --------------------------
+// All instances are solved as ONE system: global vertex = instance vertex offset + mesh vertex.
+// A scene of 1000 instances then costs ~100 CG iterations of a few launches each instead of
+// 1000 separate solves (config 4: 5.8 s -> see DESIGN.md §4.4).
+struct LsInst {
+  float xf[12];
+  const uint32_t* tris;   // mesh triangles (mesh-local vertex indices)
+  const float* verts;
+  const uint32_t* topo;   // interior-edge topology of the mesh: (i, j, p, q) per edge, mesh-local
+  uint64_t sample_begin;
+  uint64_t tri_begin;     // first global triangle of the instance
+  uint64_t edge_begin;    // first global edge
+  uint32_t vert_begin;    // first global vertex
+  uint32_t num_tris;
+  uint32_t num_edges;
+  uint32_t pad;
+};
+template <typename KeyFn>
+__device__ __forceinline__ uint32_t ls_find(uint32_t n_inst, uint64_t key, KeyFn begin_of) {
+  uint32_t lo = 0, hi = n_inst;
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (begin_of(mid) <= key) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+__global__ void k_ls_gtris(const LsInst* __restrict__ inst, uint32_t n_inst, uint64_t NT, uint32_t* __restrict__ gtris) {
+  const uint64_t gt = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gt >= NT) return;
+  const LsInst& I = inst[ls_find(n_inst, gt, [&](uint32_t m) { return inst[m].tri_begin; })];
+  const uint64_t tl = gt - I.tri_begin;
+#pragma unroll
+  for (int c = 0; c < 3; c++) gtris[3 * gt + c] = I.tris[3 * tl + c] + I.vert_begin;
+}
+__global__ void k_ls_mass_b(const AoSampleInfo* __restrict__ info, const float* __restrict__ ao, uint64_t n_samples,
+                            const LsInst* __restrict__ inst, uint32_t n_inst, const uint32_t* __restrict__ gtris,
+                            double* __restrict__ Mt, double* __restrict__ rhs) {
+  const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_samples) return;
+  const LsInst& I = inst[ls_find(n_inst, s, [&](uint32_t m) { return inst[m].sample_begin; })];
+  const AoSampleInfo si = info[s];
+  const uint64_t gt = I.tri_begin + si.tri_idx;
+  const double dA = si.dA, a = ao[s], b0 = si.bary[0], b1 = si.bary[1], b2 = si.bary[2];
+  double* M = Mt + 6 * gt;
+  atomicAdd(&M[0], dA * b0 * b0); atomicAdd(&M[1], dA * b0 * b1); atomicAdd(&M[2], dA * b0 * b2);
+  atomicAdd(&M[3], dA * b1 * b1); atomicAdd(&M[4], dA * b1 * b2); atomicAdd(&M[5], dA * b2 * b2);
+  const uint32_t* idx = gtris + 3 * gt;
+  atomicAdd(&rhs[idx[0]], dA * a * b0); atomicAdd(&rhs[idx[1]], dA * a * b1); atomicAdd(&rhs[idx[2]], dA * a * b2);
+}
+// interior-edge topology of one mesh from its sorted half-edges: the first of a run of >= 2 equal
+// keys emits (i, j, p, q); non-manifold edges pair their first two triangles (decision #6)
+__global__ void k_ls_topo(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t nH,
+                          const uint32_t* __restrict__ tris, uint32_t* __restrict__ topo, uint32_t* __restrict__ count) {
   const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k + 1 >= nH) return;
   const uint64_t key = keys[k];
   if (key == ~0ull) return;
   if (k > 0 && keys[k - 1] == key) return;
   if (keys[k + 1] != key) return;
-  LsEdge E;
-  E.i = (uint32_t)(key >> 32);
-  E.j = (uint32_t)(key & 0xffffffffu);
   const uint32_t h0 = vals[k], h1 = vals[k + 1];
-  E.p = tris[3ull * (h0 / 3) + (h0 % 3 + 2) % 3];
-  E.q = tris[3ull * (h1 / 3) + (h1 % 3 + 2) % 3];
-  auto W = [&](uint32_t v) { return xf_point(xf.m, v3(verts[3ull * v], verts[3ull * v + 1], verts[3ull * v + 2])); };
-  const V3 pi = W(E.i), pj = W(E.j), pp = W(E.p), pq = W(E.q);
+  const uint32_t e = atomicAdd(count, 1u);
+  topo[4ull * e] = (uint32_t)(key >> 32);
+  topo[4ull * e + 1] = (uint32_t)(key & 0xffffffffu);
+  topo[4ull * e + 2] = tris[3ull * (h0 / 3) + (h0 % 3 + 2) % 3];
+  topo[4ull * e + 3] = tris[3ull * (h1 / 3) + (h1 % 3 + 2) % 3];
+}
+// coefficients of the co-normal-derivative jump for every (instance, interior edge), world space
+__global__ void k_ls_edge_coeffs(const LsInst* __restrict__ inst, uint32_t n_inst, uint64_t NE, LsEdge* __restrict__ edges) {
+  const uint64_t ge = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ge >= NE) return;
+  const LsInst& I = inst[ls_find(n_inst, ge, [&](uint32_t m) { return inst[m].edge_begin; })];
+  const uint32_t* tp = I.topo + 4 * (ge - I.edge_begin);
+  LsEdge E;
+  const uint32_t li = tp[0], lj = tp[1], lp = tp[2], lq = tp[3];
+  E.i = li + I.vert_begin; E.j = lj + I.vert_begin; E.p = lp + I.vert_begin; E.q = lq + I.vert_begin;
+  E.c[0] = E.c[1] = E.c[2] = E.c[3] = 0.0;
+  auto W = [&](uint32_t v) { return xf_point(I.xf, v3(I.verts[3ull * v], I.verts[3ull * v + 1], I.verts[3ull * v + 2])); };
+  const V3 pi = W(li), pj = W(lj), pp = W(lp), pq = W(lq);
   const double ex_ = (double)pj.x - pi.x, ey_ = (double)pj.y - pi.y, ez_ = (double)pj.z - pi.z;
   const double L2 = ex_ * ex_ + ey_ * ey_ + ez_ * ez_;
-  if (!(L2 > 0.0)) return;
-  double s[2], h[2], A[2];
-  const V3 opp[2] = {pp, pq};
+  if (L2 > 0.0) {
+    double s[2], h[2], A[2];
+    const V3 opp[2] = {pp, pq};
 #pragma unroll
-  for (int m = 0; m < 2; m++) {
-    const double ox = (double)opp[m].x - pi.x, oy = (double)opp[m].y - pi.y, oz = (double)opp[m].z - pi.z;
-    s[m] = (ox * ex_ + oy * ey_ + oz * ez_) / L2;
-    const double rx = ox - s[m] * ex_, ry = oy - s[m] * ey_, rz = oz - s[m] * ez_;
-    h[m] = sqrt(rx * rx + ry * ry + rz * rz);
-    A[m] = 0.5 * sqrt(L2) * h[m];
+    for (int m = 0; m < 2; m++) {
+      const double ox = (double)opp[m].x - pi.x, oy = (double)opp[m].y - pi.y, oz = (double)opp[m].z - pi.z;
+      s[m] = (ox * ex_ + oy * ey_ + oz * ez_) / L2;
+      const double rx = ox - s[m] * ex_, ry = oy - s[m] * ey_, rz = oz - s[m] * ez_;
+      h[m] = sqrt(rx * rx + ry * ry + rz * rz);
+      A[m] = 0.5 * sqrt(L2) * h[m];
+    }
+    if (h[0] > 0.0 && h[1] > 0.0) {
+      const double w = A[0] + A[1];
+      E.c[0] = w * ((1.0 - s[0]) / h[0] + (1.0 - s[1]) / h[1]);
+      E.c[1] = w * (s[0] / h[0] + s[1] / h[1]);
+      E.c[2] = w * (-1.0 / h[0]);
+      E.c[3] = w * (-1.0 / h[1]);
+    }
   }
-  if (!(h[0] > 0.0 && h[1] > 0.0)) return;
-  const double w = A[0] + A[1];
-  E.c[0] = w * ((1.0 - s[0]) / h[0] + (1.0 - s[1]) / h[1]);
-  E.c[1] = w * (s[0] / h[0] + s[1] / h[1]);
-  E.c[2] = w * (-1.0 / h[0]);
-  E.c[3] = w * (-1.0 / h[1]);
-  edges[atomicAdd(edge_count, 1u)] = E;
+  edges[ge] = E;   // degenerate edges keep zero coefficients: a no-op in y = (M + wR) x
 }
+
 // diagonal of the sampled mass matrix (lumped-mass test and the Jacobi preconditioner)
 __global__ void k_ls_diag_mass(const uint32_t* __restrict__ tris, uint64_t nT, const double* __restrict__ Mt, double* __restrict__ diag) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

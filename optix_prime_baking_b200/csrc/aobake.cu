@@ -968,6 +968,137 @@ int aobake_get_hit_counts(AoBake* ctx, uint32_t* host_counts) {
   return AOBAKE_OK;
 }
 
+}  // extern "C"
+
+namespace {
+
+// bake_filter_least_squares.cpp: (M + w R) x = b, fp64, for ALL instances as one block-diagonal
+// system, matrix-free Jacobi-PCG.
+int ls_filter_batched(AoBake* ctx, float weight, float* const* host_vertex_ao) {
+  cudaStream_t st = ctx->stream;
+  const uint32_t nI = (uint32_t)ctx->insts.size();
+  const double w = weight;
+  // ---- interior-edge topology, once per mesh that is instanced ----
+  const size_t nM = ctx->meshes.size();
+  std::vector<DBuf<uint32_t>> topo(nM);
+  std::vector<uint32_t> topo_count(nM, 0);
+  std::vector<char> used(nM, 0);
+  for (const HostInstance& I : ctx->insts) used[I.mesh] = 1;
+  if (weight != 0.0f) {
+    for (size_t m = 0; m < nM; m++) {
+      const DeviceMesh& M = ctx->meshes[m];
+      if (!used[m] || !M.nT) continue;
+      const uint64_t nH = 3 * M.nT;
+      DBuf<uint64_t> keys, keys_s;
+      DBuf<uint32_t> vals, vals_s, cnt;
+      CK(keys.alloc(nH)); CK(keys_s.alloc(nH)); CK(vals.alloc(nH)); CK(vals_s.alloc(nH)); CK(cnt.alloc(1));
+      CK(topo[m].alloc(4 * (nH / 2 + 1)));
+      CK(cudaMemsetAsync(cnt.p, 0, sizeof(uint32_t), st));
+      k_ls_halfedges<<<grid_for(nH, 256), 256, 0, st>>>(M.tris.p, M.nT, keys.p, vals.p);
+      CKL();
+      size_t tmp_bytes = 0;
+      CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.p, keys_s.p, vals.p, vals_s.p, (long long)nH, 0, 64, st));
+      DBuf<uint8_t> tmp;
+      CK(tmp.alloc(tmp_bytes));
+      CK(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys.p, keys_s.p, vals.p, vals_s.p, (long long)nH, 0, 64, st));
+      k_ls_topo<<<grid_for(nH, 256), 256, 0, st>>>(keys_s.p, vals_s.p, nH, M.tris.p, topo[m].p, cnt.p);
+      CKL();
+      CK(cudaMemcpyAsync(&topo_count[m], cnt.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+    }
+  }
+  // ---- instance descriptors and global numbering ----
+  std::vector<LsInst> h(std::max(nI, 1u));
+  std::vector<uint64_t> vbase(nI + 1, 0);
+  uint64_t NV = 0, NT = 0, NE = 0, NS = 0;
+  for (uint32_t i = 0; i < nI; i++) {
+    const HostInstance& I = ctx->insts[i];
+    const DeviceMesh& M = ctx->meshes[I.mesh];
+    LsInst& L = h[i];
+    memcpy(L.xf, I.xf, sizeof(L.xf));
+    L.tris = M.tris.p; L.verts = M.verts.p; L.topo = topo[I.mesh].p;
+    L.sample_begin = NS; L.tri_begin = NT; L.edge_begin = NE; L.vert_begin = (uint32_t)NV;
+    L.num_tris = (uint32_t)M.nT; L.num_edges = topo_count[I.mesh]; L.pad = 0;
+    vbase[i] = NV;
+    NS += ctx->per_instance[i]; NT += M.nT; NE += topo_count[I.mesh]; NV += M.nV;
+  }
+  vbase[nI] = NV;
+  if (NV > 0xfffffff0ull || NE > 0xfffffff0ull) return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "least-squares system too large for 32-bit indices");
+  if (NS != ctx->num_samples) return ctx->fail(AOBAKE_ERR_STATE, "per-instance sample counts do not add up to the resident samples");
+  const uint64_t v1 = std::max<uint64_t>(NV, 1), t1 = std::max<uint64_t>(NT, 1);
+  DBuf<LsInst> d_inst;
+  DBuf<uint32_t> gtris;
+  DBuf<double> Mt, rhs, diag, x, r, z, p, Ap, scal;
+  DBuf<uint8_t> fixed;
+  DBuf<LsEdge> edges;
+  DBuf<float> d_out;
+  CK(d_inst.alloc(std::max(nI, 1u))); CK(gtris.alloc(3 * t1)); CK(Mt.alloc(6 * t1)); CK(rhs.alloc(v1)); CK(diag.alloc(v1));
+  CK(x.alloc(v1)); CK(r.alloc(v1)); CK(z.alloc(v1)); CK(p.alloc(v1)); CK(Ap.alloc(v1)); CK(scal.alloc(8)); CK(fixed.alloc(v1));
+  CK(edges.alloc(std::max<uint64_t>(NE, 1))); CK(d_out.alloc(v1));
+  if (nI) CK(cudaMemcpyAsync(d_inst.p, h.data(), nI * sizeof(LsInst), cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(Mt.p, 0, Mt.n * sizeof(double), st));
+  CK(cudaMemsetAsync(rhs.p, 0, v1 * sizeof(double), st));
+  CK(cudaMemsetAsync(diag.p, 0, v1 * sizeof(double), st));
+  if (NT) k_ls_gtris<<<grid_for(NT, 256), 256, 0, st>>>(d_inst.p, nI, NT, gtris.p);
+  if (NS) k_ls_mass_b<<<grid_for(NS, 256), 256, 0, st>>>(ctx->d_info.p, ctx->d_ao.p, NS, d_inst.p, nI, gtris.p, Mt.p, rhs.p);
+  if (NE) k_ls_edge_coeffs<<<grid_for(NE, 256), 256, 0, st>>>(d_inst.p, nI, NE, edges.p);
+  if (NT) k_ls_diag_mass<<<grid_for(NT, 256), 256, 0, st>>>(gtris.p, NT, Mt.p, diag.p);
+  if (NV) k_ls_fix<<<grid_for(NV, 256), 256, 0, st>>>(diag.p, rhs.p, fixed.p, NV);
+  if (NE) k_ls_diag_edges<<<grid_for(NE, 256), 256, 0, st>>>(edges.p, (uint32_t)NE, w, diag.p);
+  if (NV) k_ls_init<<<grid_for(NV, 256), 256, 0, st>>>(rhs.p, diag.p, r.p, z.p, p.p, x.p, NV);
+  CKL();
+  // scal: [0]=|b|^2 [1]=rz_old [2]=pAp [3]=rz_new [4]=|r|^2
+  const unsigned dot_grid = std::min<unsigned>(grid_for(v1, 256), (unsigned)ctx->sm_count * 8u);
+  const uint64_t nwork = std::max<uint64_t>(NT, NE);
+  CK(cudaMemsetAsync(scal.p, 0, 8 * sizeof(double), st));
+  if (NV) {
+    k_dot<<<dot_grid, 256, 0, st>>>(rhs.p, rhs.p, NV, scal.p + 0);
+    k_dot<<<dot_grid, 256, 0, st>>>(r.p, z.p, NV, scal.p + 1);
+  }
+  double hs[8];
+  CK(cudaMemcpyAsync(hs, scal.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const double bnorm2 = hs[0];
+  int it = 0;
+  if (NV && bnorm2 > 0.0) {
+    const double tol2 = (double)ctx->params.cg_tolerance * (double)ctx->params.cg_tolerance * bnorm2;
+    double rr = bnorm2;
+    for (; it < ctx->params.cg_max_iterations && rr > tol2; it++) {
+      CK(cudaMemsetAsync(Ap.p, 0, NV * sizeof(double), st));
+      CK(cudaMemsetAsync(scal.p + 2, 0, 3 * sizeof(double), st));
+      if (nwork) k_ls_apply<<<grid_for(nwork, 256), 256, 0, st>>>(gtris.p, NT, Mt.p, edges.p, (uint32_t)NE, w, p.p, Ap.p);
+      k_ls_fix_apply<<<grid_for(NV, 256), 256, 0, st>>>(fixed.p, p.p, Ap.p, NV);
+      k_dot<<<dot_grid, 256, 0, st>>>(p.p, Ap.p, NV, scal.p + 2);
+      k_ls_update<<<grid_for(NV, 256), 256, 0, st>>>(scal.p, 1, 2, p.p, Ap.p, diag.p, x.p, r.p, z.p, NV);
+      k_dot<<<dot_grid, 256, 0, st>>>(r.p, z.p, NV, scal.p + 3);
+      k_dot<<<dot_grid, 256, 0, st>>>(r.p, r.p, NV, scal.p + 4);
+      k_ls_dir<<<grid_for(NV, 256), 256, 0, st>>>(scal.p, 3, 1, z.p, p.p, NV);
+      CKL();
+      CK(cudaMemcpyAsync(hs, scal.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      if (!(hs[2] > 0.0)) return ctx->fail(AOBAKE_ERR_SOLVER, "CG breakdown: p.Ap = %g at iteration %d", hs[2], it);
+      rr = hs[4];
+      CK(cudaMemcpyAsync(scal.p + 1, scal.p + 3, sizeof(double), cudaMemcpyDeviceToDevice, st));
+    }
+    if (rr > tol2) return ctx->fail(AOBAKE_ERR_SOLVER, "CG did not reach %g in %d iterations (|r|/|b| = %g)", (double)ctx->params.cg_tolerance, it, sqrt(rr / bnorm2));
+  } else if (NV) {
+    CK(cudaMemsetAsync(x.p, 0, NV * sizeof(double), st));
+  }
+  ctx->timings.cg_iterations = it;
+  if (NV) k_d2f<<<grid_for(NV, 256), 256, 0, st>>>(x.p, d_out.p, NV);
+  CKL();
+  for (uint32_t i = 0; i < nI; i++) {
+    const uint64_t nv = vbase[i + 1] - vbase[i];
+    if (nv && host_vertex_ao[i]) CK(cudaMemcpyAsync(host_vertex_ao[i], d_out.p + vbase[i], nv * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(st));
+  return AOBAKE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
 int aobake_map_ao_to_vertices(AoBake* ctx, int mode, float weight, float* const* host_vertex_ao) {
   if (!ctx || !host_vertex_ao) return AOBAKE_ERR_INVALID_ARGUMENT;
   if (!ctx->have_scene || !ctx->have_ao) return ctx->fail(AOBAKE_ERR_STATE, "map_ao_to_vertices needs a scene and AO values");
@@ -978,111 +1109,29 @@ int aobake_map_ao_to_vertices(AoBake* ctx, int mode, float weight, float* const*
   cudaStream_t st = ctx->stream;
   CK(cudaEventRecord(ctx->ev0, st));
   ctx->timings.cg_iterations = 0;
-  uint64_t base = 0;
-  for (size_t ii = 0; ii < ctx->insts.size(); ii++) {
-    const HostInstance& I = ctx->insts[ii];
-    const DeviceMesh& m = ctx->meshes[I.mesh];
-    const uint64_t nV = m.nV, nT = m.nT, cnt = ctx->per_instance[ii];
-    DBuf<float> d_out;
-    CK(d_out.alloc(std::max<uint64_t>(nV, 1)));
-    if (mode == AOBAKE_FILTER_AREA_BASED) {
+  if (mode == AOBAKE_FILTER_LEAST_SQUARES) {
+    const int rc = ls_filter_batched(ctx, weight, host_vertex_ao);
+    if (rc) return rc;
+  } else {
+    // bake_filter.cpp filter_mesh, per instance
+    uint64_t base = 0;
+    for (size_t ii = 0; ii < ctx->insts.size(); ii++) {
+      const HostInstance& I = ctx->insts[ii];
+      const DeviceMesh& m = ctx->meshes[I.mesh];
+      const uint64_t nV = m.nV, cnt = ctx->per_instance[ii];
+      DBuf<float> d_out;
       DBuf<double> num, wgt;
+      CK(d_out.alloc(std::max<uint64_t>(nV, 1)));
       CK(num.alloc(std::max<uint64_t>(nV, 1))); CK(wgt.alloc(std::max<uint64_t>(nV, 1)));
       CK(cudaMemsetAsync(num.p, 0, num.n * sizeof(double), st));
       CK(cudaMemsetAsync(wgt.p, 0, wgt.n * sizeof(double), st));
       if (cnt) k_area_scatter<<<grid_for(cnt, 256), 256, 0, st>>>(ctx->d_info.p, ctx->d_ao.p, base, cnt, m.tris.p, num.p, wgt.p);
       if (nV) k_area_final<<<grid_for(nV, 256), 256, 0, st>>>(num.p, wgt.p, nV, d_out.p);
       CKL();
+      if (nV && host_vertex_ao[ii]) CK(cudaMemcpyAsync(host_vertex_ao[ii], d_out.p, nV * sizeof(float), cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
-    } else {
-      // matrix-free Jacobi-PCG on (M + w R) x = b, fp64
-      const double w = weight;
-      DBuf<double> Mt, rhs, diag, x, r, z, p, Ap, scal;
-      DBuf<uint8_t> fixed;
-      DBuf<LsEdge> edges;
-      DBuf<uint32_t> ecount;
-      const uint64_t v1 = std::max<uint64_t>(nV, 1);
-      CK(Mt.alloc(6 * std::max<uint64_t>(nT, 1))); CK(rhs.alloc(v1)); CK(diag.alloc(v1)); CK(x.alloc(v1)); CK(r.alloc(v1)); CK(z.alloc(v1));
-      CK(p.alloc(v1)); CK(Ap.alloc(v1)); CK(scal.alloc(8)); CK(fixed.alloc(v1)); CK(ecount.alloc(1));
-      CK(cudaMemsetAsync(Mt.p, 0, Mt.n * sizeof(double), st));
-      CK(cudaMemsetAsync(rhs.p, 0, v1 * sizeof(double), st));
-      CK(cudaMemsetAsync(diag.p, 0, v1 * sizeof(double), st));
-      CK(cudaMemsetAsync(ecount.p, 0, sizeof(uint32_t), st));
-      if (cnt) k_ls_mass<<<grid_for(cnt, 256), 256, 0, st>>>(ctx->d_info.p, ctx->d_ao.p, base, cnt, m.tris.p, Mt.p, rhs.p);
-      CKL();
-      uint32_t nE = 0;
-      if (weight != 0.0f && nT) {
-        const uint64_t nH = 3 * nT;
-        DBuf<uint64_t> keys, keys_s;
-        DBuf<uint32_t> vals, vals_s;
-        CK(keys.alloc(nH)); CK(keys_s.alloc(nH)); CK(vals.alloc(nH)); CK(vals_s.alloc(nH));
-        k_ls_halfedges<<<grid_for(nH, 256), 256, 0, st>>>(m.tris.p, nT, keys.p, vals.p);
-        CKL();
-        size_t tmp_bytes = 0;
-        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.p, keys_s.p, vals.p, vals_s.p, (long long)nH, 0, 64, st));
-        DBuf<uint8_t> tmp;
-        CK(tmp.alloc(tmp_bytes));
-        CK(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys.p, keys_s.p, vals.p, vals_s.p, (long long)nH, 0, 64, st));
-        CK(edges.alloc(nH / 2 + 1));
-        Xf12 xf;
-        memcpy(xf.m, I.xf, sizeof(xf.m));
-        k_ls_edges<<<grid_for(nH, 256), 256, 0, st>>>(keys_s.p, vals_s.p, nH, m.tris.p, m.verts.p, xf, edges.p, ecount.p);
-        CKL();
-        CK(cudaMemcpyAsync(&nE, ecount.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-      }
-      const uint64_t nwork = std::max<uint64_t>(nT, nE);
-      if (nT) k_ls_diag_mass<<<grid_for(nT, 256), 256, 0, st>>>(m.tris.p, nT, Mt.p, diag.p);
-      if (nV) k_ls_fix<<<grid_for(nV, 256), 256, 0, st>>>(diag.p, rhs.p, fixed.p, nV);
-      if (nE) k_ls_diag_edges<<<grid_for(nE, 256), 256, 0, st>>>(edges.p, nE, w, diag.p);
-      if (nV) {
-        k_ls_init<<<grid_for(nV, 256), 256, 0, st>>>(rhs.p, diag.p, r.p, z.p, p.p, x.p, nV);
-      }
-      CKL();
-      // scal: [0]=|b|^2 [1]=rz_old [2]=pAp [3]=rz_new [4]=|r|^2
-      const unsigned dot_grid = std::min<unsigned>(grid_for(v1, 256), (unsigned)ctx->sm_count * 8u);
-      CK(cudaMemsetAsync(scal.p, 0, 8 * sizeof(double), st));
-      if (nV) {
-        k_dot<<<dot_grid, 256, 0, st>>>(rhs.p, rhs.p, nV, scal.p + 0);
-        k_dot<<<dot_grid, 256, 0, st>>>(r.p, z.p, nV, scal.p + 1);
-      }
-      double hs[8];
-      CK(cudaMemcpyAsync(hs, scal.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
-      CK(cudaStreamSynchronize(st));
-      const double bnorm2 = hs[0];
-      int it = 0;
-      if (nV && bnorm2 > 0.0) {
-        const double tol2 = (double)ctx->params.cg_tolerance * (double)ctx->params.cg_tolerance * bnorm2;
-        double rr = bnorm2;
-        for (; it < ctx->params.cg_max_iterations && rr > tol2; it++) {
-          CK(cudaMemsetAsync(Ap.p, 0, nV * sizeof(double), st));
-          CK(cudaMemsetAsync(scal.p + 2, 0, 3 * sizeof(double), st));
-          if (nwork) k_ls_apply<<<grid_for(nwork, 256), 256, 0, st>>>(m.tris.p, nT, Mt.p, edges.p, nE, w, p.p, Ap.p);
-          k_ls_fix_apply<<<grid_for(nV, 256), 256, 0, st>>>(fixed.p, p.p, Ap.p, nV);
-          k_dot<<<dot_grid, 256, 0, st>>>(p.p, Ap.p, nV, scal.p + 2);
-          k_ls_update<<<grid_for(nV, 256), 256, 0, st>>>(scal.p, 1, 2, p.p, Ap.p, diag.p, x.p, r.p, z.p, nV);
-          k_dot<<<dot_grid, 256, 0, st>>>(r.p, z.p, nV, scal.p + 3);
-          k_dot<<<dot_grid, 256, 0, st>>>(r.p, r.p, nV, scal.p + 4);
-          k_ls_dir<<<grid_for(nV, 256), 256, 0, st>>>(scal.p, 3, 1, z.p, p.p, nV);
-          CKL();
-          CK(cudaMemcpyAsync(hs, scal.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
-          CK(cudaStreamSynchronize(st));
-          if (!(hs[2] > 0.0)) return ctx->fail(AOBAKE_ERR_SOLVER, "CG breakdown: p.Ap = %g at iteration %d", hs[2], it);
-          rr = hs[4];
-          CK(cudaMemcpyAsync(scal.p + 1, scal.p + 3, sizeof(double), cudaMemcpyDeviceToDevice, st));
-        }
-        if (rr > tol2) return ctx->fail(AOBAKE_ERR_SOLVER, "CG did not reach %g in %d iterations (|r|/|b| = %g)", (double)ctx->params.cg_tolerance, it, sqrt(rr / bnorm2));
-      } else if (nV) {
-        CK(cudaMemsetAsync(x.p, 0, nV * sizeof(double), st));
-      }
-      ctx->timings.cg_iterations += it;
-      if (nV) k_d2f<<<grid_for(nV, 256), 256, 0, st>>>(x.p, d_out.p, nV);
-      CKL();
-      CK(cudaStreamSynchronize(st));
+      base += cnt;
     }
-    if (nV && host_vertex_ao[ii]) CK(cudaMemcpyAsync(host_vertex_ao[ii], d_out.p, nV * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    base += cnt;
   }
   CK(cudaEventRecord(ctx->ev1, st));
   CK(cudaStreamSynchronize(st));
