@@ -654,20 +654,6 @@ __global__ void k_ao_finalize(const uint32_t* __restrict__ hits, uint64_t n, flo
 // ---------------------------------------------------------------------------------------
 // Vertex maps
 // ---------------------------------------------------------------------------------------
-// bake_filter.cpp filter_mesh: scatter ao*bary*dA and bary*dA (fp64 atomics), then divide.
-__global__ void k_area_scatter(const AoSampleInfo* __restrict__ info, const float* __restrict__ ao, uint64_t begin, uint64_t count,
-                               const uint32_t* __restrict__ tris, double* __restrict__ num, double* __restrict__ wgt) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
-  const AoSampleInfo si = info[begin + i];
-  const double dA = si.dA, val = (double)ao[begin + i] * dA;
-#pragma unroll
-  for (int c = 0; c < 3; c++) {
-    const uint32_t v = tris[3ull * si.tri_idx + c];
-    atomicAdd(&num[v], (double)si.bary[c] * val);
-    atomicAdd(&wgt[v], (double)si.bary[c] * dA);
-  }
-}
 __global__ void k_area_final(const double* __restrict__ num, const double* __restrict__ wgt, uint64_t nV, float* __restrict__ out) {
   const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= nV) return;
@@ -714,6 +700,22 @@ __device__ __forceinline__ uint32_t ls_find(uint32_t n_inst, uint64_t key, KeyFn
     if (begin_of(mid) <= key) lo = mid; else hi = mid;
   }
   return lo;
+}
+// bake_filter.cpp filter_mesh for all instances at once: scatter ao*bary*dA and bary*dA to the three
+// (global) vertices of the sample's triangle with fp64 atomics; k_area_final divides.
+__global__ void k_area_scatter_b(const AoSampleInfo* __restrict__ info, const float* __restrict__ ao, uint64_t n_samples,
+                                 const LsInst* __restrict__ inst, uint32_t n_inst, double* __restrict__ num, double* __restrict__ wgt) {
+  const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_samples) return;
+  const LsInst& I = inst[ls_find(n_inst, s, [&](uint32_t m) { return inst[m].sample_begin; })];
+  const AoSampleInfo si = info[s];
+  const double dA = si.dA, val = (double)ao[s] * dA;
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    const uint32_t v = I.tris[3ull * si.tri_idx + c] + I.vert_begin;
+    atomicAdd(&num[v], (double)si.bary[c] * val);
+    atomicAdd(&wgt[v], (double)si.bary[c] * dA);
+  }
 }
 __global__ void k_ls_gtris(const LsInst* __restrict__ inst, uint32_t n_inst, uint64_t NT, uint32_t* __restrict__ gtris) {
   const uint64_t gt = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

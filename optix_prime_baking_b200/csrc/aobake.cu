@@ -135,6 +135,7 @@ struct AoBake {
   DBuf<unsigned long long> d_stats;
   DBuf<unsigned long long> d_counter;
   bool have_ao = false;
+  bool have_infos = false;           // sample_infos (tri_idx, bary, dA) are resident — needed by the vertex maps
 
   AoTimings timings{};
 
@@ -316,6 +317,7 @@ int ensure_areas(AoBake* ctx) {
 int alloc_samples(AoBake* ctx, uint64_t n) {
   ctx->num_samples = n;
   ctx->have_ao = false;
+  ctx->have_infos = false;
   const uint64_t m = std::max<uint64_t>(n, 1);
   CK(ctx->d_pos.alloc(3 * m)); CK(ctx->d_nrm.alloc(3 * m)); CK(ctx->d_fnrm.alloc(3 * m)); CK(ctx->d_info.alloc(m));
   CK(ctx->d_ao.alloc(m)); CK(ctx->d_hits.alloc(m));
@@ -774,6 +776,7 @@ int aobake_sample_instances(AoBake* ctx, const size_t* per_instance, size_t min_
     k_place_samples<<<grid_for(total, 256), 256, 0, st>>>(ctx->d_inst.p, ni, E, final_off.p, final_cnt.p, ctx->d_tri_area.p, total, ctx->d_pos.p,
                                                          ctx->d_nrm.p, ctx->d_fnrm.p, ctx->d_info.p);
     CKL();
+    ctx->have_infos = true;
     CK(cudaStreamSynchronize(st));
   }
   CK(cudaEventRecord(ctx->ev1, st));
@@ -810,7 +813,10 @@ int aobake_set_samples(AoBake* ctx, const AoSamples* s, const size_t* per_instan
     CK(cudaMemcpyAsync(ctx->d_pos.p, s->sample_positions, 12 * n, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->d_nrm.p, s->sample_normals, 12 * n, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->d_fnrm.p, s->sample_face_normals, 12 * n, cudaMemcpyHostToDevice, st));
-    if (s->sample_infos) CK(cudaMemcpyAsync(ctx->d_info.p, s->sample_infos, sizeof(AoSampleInfo) * n, cudaMemcpyHostToDevice, st));
+    if (s->sample_infos) {
+      CK(cudaMemcpyAsync(ctx->d_info.p, s->sample_infos, sizeof(AoSampleInfo) * n, cudaMemcpyHostToDevice, st));
+      ctx->have_infos = true;
+    }
     CK(cudaStreamSynchronize(st));
   }
   return AOBAKE_OK;
@@ -972,6 +978,58 @@ int aobake_get_hit_counts(AoBake* ctx, uint32_t* host_counts) {
 
 namespace {
 
+// Global numbering shared by both vertex maps: instance i owns vertices [vbase[i], vbase[i+1]),
+// triangles, samples and (least squares) interior edges in consecutive global ranges.
+void build_filter_instances(AoBake* ctx, const std::vector<DBuf<uint32_t>>* topo, const std::vector<uint32_t>* topo_count,
+                            std::vector<LsInst>& h, std::vector<uint64_t>& vbase, uint64_t* NV, uint64_t* NT, uint64_t* NE, uint64_t* NS) {
+  const uint32_t nI = (uint32_t)ctx->insts.size();
+  h.assign(std::max(nI, 1u), LsInst{});
+  vbase.assign(nI + 1, 0);
+  uint64_t nv = 0, nt = 0, ne = 0, ns = 0;
+  for (uint32_t i = 0; i < nI; i++) {
+    const HostInstance& I = ctx->insts[i];
+    const DeviceMesh& M = ctx->meshes[I.mesh];
+    LsInst& L = h[i];
+    memcpy(L.xf, I.xf, sizeof(L.xf));
+    L.tris = M.tris.p; L.verts = M.verts.p; L.topo = topo ? (*topo)[I.mesh].p : nullptr;
+    L.sample_begin = ns; L.tri_begin = nt; L.edge_begin = ne; L.vert_begin = (uint32_t)nv;
+    L.num_tris = (uint32_t)M.nT; L.num_edges = topo_count ? (*topo_count)[I.mesh] : 0u; L.pad = 0;
+    vbase[i] = nv;
+    ns += ctx->per_instance[i]; nt += M.nT; ne += L.num_edges; nv += M.nV;
+  }
+  vbase[nI] = nv;
+  *NV = nv; *NT = nt; *NE = ne; *NS = ns;
+}
+
+// bake_filter.cpp filter / filter_mesh for all instances in one pass.
+int area_filter_batched(AoBake* ctx, float* const* host_vertex_ao) {
+  cudaStream_t st = ctx->stream;
+  const uint32_t nI = (uint32_t)ctx->insts.size();
+  std::vector<LsInst> h;
+  std::vector<uint64_t> vbase;
+  uint64_t NV = 0, NT = 0, NE = 0, NS = 0;
+  build_filter_instances(ctx, nullptr, nullptr, h, vbase, &NV, &NT, &NE, &NS);
+  if (NV > 0xfffffff0ull) return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "too many vertices for 32-bit indices");
+  if (NS != ctx->num_samples) return ctx->fail(AOBAKE_ERR_STATE, "per-instance sample counts do not add up to the resident samples");
+  const uint64_t v1 = std::max<uint64_t>(NV, 1);
+  DBuf<LsInst> d_inst;
+  DBuf<double> num, wgt;
+  DBuf<float> d_out;
+  CK(d_inst.alloc(std::max(nI, 1u))); CK(num.alloc(v1)); CK(wgt.alloc(v1)); CK(d_out.alloc(v1));
+  if (nI) CK(cudaMemcpyAsync(d_inst.p, h.data(), nI * sizeof(LsInst), cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(num.p, 0, v1 * sizeof(double), st));
+  CK(cudaMemsetAsync(wgt.p, 0, v1 * sizeof(double), st));
+  if (NS) k_area_scatter_b<<<grid_for(NS, 256), 256, 0, st>>>(ctx->d_info.p, ctx->d_ao.p, NS, d_inst.p, nI, num.p, wgt.p);
+  if (NV) k_area_final<<<grid_for(NV, 256), 256, 0, st>>>(num.p, wgt.p, NV, d_out.p);
+  CKL();
+  for (uint32_t i = 0; i < nI; i++) {
+    const uint64_t nv = vbase[i + 1] - vbase[i];
+    if (nv && host_vertex_ao[i]) CK(cudaMemcpyAsync(host_vertex_ao[i], d_out.p + vbase[i], nv * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(st));
+  return AOBAKE_OK;
+}
+
 // bake_filter_least_squares.cpp: (M + w R) x = b, fp64, for ALL instances as one block-diagonal
 // system, matrix-free Jacobi-PCG.
 int ls_filter_batched(AoBake* ctx, float weight, float* const* host_vertex_ao) {
@@ -1008,21 +1066,10 @@ int ls_filter_batched(AoBake* ctx, float weight, float* const* host_vertex_ao) {
     }
   }
   // ---- instance descriptors and global numbering ----
-  std::vector<LsInst> h(std::max(nI, 1u));
-  std::vector<uint64_t> vbase(nI + 1, 0);
+  std::vector<LsInst> h;
+  std::vector<uint64_t> vbase;
   uint64_t NV = 0, NT = 0, NE = 0, NS = 0;
-  for (uint32_t i = 0; i < nI; i++) {
-    const HostInstance& I = ctx->insts[i];
-    const DeviceMesh& M = ctx->meshes[I.mesh];
-    LsInst& L = h[i];
-    memcpy(L.xf, I.xf, sizeof(L.xf));
-    L.tris = M.tris.p; L.verts = M.verts.p; L.topo = topo[I.mesh].p;
-    L.sample_begin = NS; L.tri_begin = NT; L.edge_begin = NE; L.vert_begin = (uint32_t)NV;
-    L.num_tris = (uint32_t)M.nT; L.num_edges = topo_count[I.mesh]; L.pad = 0;
-    vbase[i] = NV;
-    NS += ctx->per_instance[i]; NT += M.nT; NE += topo_count[I.mesh]; NV += M.nV;
-  }
-  vbase[nI] = NV;
+  build_filter_instances(ctx, &topo, &topo_count, h, vbase, &NV, &NT, &NE, &NS);
   if (NV > 0xfffffff0ull || NE > 0xfffffff0ull) return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "least-squares system too large for 32-bit indices");
   if (NS != ctx->num_samples) return ctx->fail(AOBAKE_ERR_STATE, "per-instance sample counts do not add up to the resident samples");
   const uint64_t v1 = std::max<uint64_t>(NV, 1), t1 = std::max<uint64_t>(NT, 1);
@@ -1103,6 +1150,7 @@ int aobake_map_ao_to_vertices(AoBake* ctx, int mode, float weight, float* const*
   if (!ctx || !host_vertex_ao) return AOBAKE_ERR_INVALID_ARGUMENT;
   if (!ctx->have_scene || !ctx->have_ao) return ctx->fail(AOBAKE_ERR_STATE, "map_ao_to_vertices needs a scene and AO values");
   if (ctx->per_instance.size() != ctx->insts.size()) return ctx->fail(AOBAKE_ERR_STATE, "per-instance sample counts unknown (pass them to set_samples)");
+  if (ctx->num_samples && !ctx->have_infos) return ctx->fail(AOBAKE_ERR_STATE, "sample_infos were not uploaded (set_samples was given a null sample_infos)");
   if (mode != AOBAKE_FILTER_AREA_BASED && mode != AOBAKE_FILTER_LEAST_SQUARES) return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "invalid filter mode %d", mode);
   ScopedTimer tm(ctx);
   CK(cudaSetDevice(ctx->device));
@@ -1113,25 +1161,8 @@ int aobake_map_ao_to_vertices(AoBake* ctx, int mode, float weight, float* const*
     const int rc = ls_filter_batched(ctx, weight, host_vertex_ao);
     if (rc) return rc;
   } else {
-    // bake_filter.cpp filter_mesh, per instance
-    uint64_t base = 0;
-    for (size_t ii = 0; ii < ctx->insts.size(); ii++) {
-      const HostInstance& I = ctx->insts[ii];
-      const DeviceMesh& m = ctx->meshes[I.mesh];
-      const uint64_t nV = m.nV, cnt = ctx->per_instance[ii];
-      DBuf<float> d_out;
-      DBuf<double> num, wgt;
-      CK(d_out.alloc(std::max<uint64_t>(nV, 1)));
-      CK(num.alloc(std::max<uint64_t>(nV, 1))); CK(wgt.alloc(std::max<uint64_t>(nV, 1)));
-      CK(cudaMemsetAsync(num.p, 0, num.n * sizeof(double), st));
-      CK(cudaMemsetAsync(wgt.p, 0, wgt.n * sizeof(double), st));
-      if (cnt) k_area_scatter<<<grid_for(cnt, 256), 256, 0, st>>>(ctx->d_info.p, ctx->d_ao.p, base, cnt, m.tris.p, num.p, wgt.p);
-      if (nV) k_area_final<<<grid_for(nV, 256), 256, 0, st>>>(num.p, wgt.p, nV, d_out.p);
-      CKL();
-      if (nV && host_vertex_ao[ii]) CK(cudaMemcpyAsync(host_vertex_ao[ii], d_out.p, nV * sizeof(float), cudaMemcpyDeviceToHost, st));
-      CK(cudaStreamSynchronize(st));
-      base += cnt;
-    }
+    const int rc = area_filter_batched(ctx, host_vertex_ao);
+    if (rc) return rc;
   }
   CK(cudaEventRecord(ctx->ev1, st));
   CK(cudaStreamSynchronize(st));
