@@ -122,11 +122,23 @@ def pinned_like(a: np.ndarray) -> np.ndarray:
 out_holder = []
 
 
+def use_all_host_cores():
+    """torchrun sets OMP_NUM_THREADS=1 per rank; the CPU arm runs on rank 0 alone and takes every core."""
+    from tests.oracle_binding import lib
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().ao_oracle_set_num_threads(int(n))
+    return n
+
+
 def cpu_baseline(scene, blockers, samples, rays, off, maxd, target_rays=12_000_000):
     """The oracle (kind 'port': the reference cannot be compiled) on all host cores,
     on a bounded, strided subset of the workload's samples."""
     from tests.oracle_binding import Oracle, lib
     from optix_prime_baking_b200.ctypes_types import SampleBuffers
+    use_all_host_cores()
     q = int(np.float32(np.sqrt(np.float32(rays))) + np.float32(0.5))
     n_sub = max(1, min(samples.n, target_rays // (q * q)))
     pick = np.linspace(0, samples.n - 1, n_sub).astype(np.int64)
@@ -157,6 +169,7 @@ def run_reference(args, rank, world):
     rays = RAYS[args.workload]
     off, maxd = scenes.default_distances(scene)
     from tests.oracle_binding import Oracle, lib
+    use_all_host_cores()
     orc = Oracle(scene, blockers)
     total, per = orc.distribute_samples(min_per, requested)
     samples = orc.sample_instances(per, min_per)

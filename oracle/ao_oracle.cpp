@@ -693,6 +693,14 @@ int ao_oracle_num_threads(void) {
   return 1;
 #endif
 }
+// torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm is told to use all host cores
+void ao_oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
 uint32_t ao_oracle_tea(uint32_t rounds, uint32_t v0, uint32_t v1) { return tea(rounds, v0, v1); }
 uint32_t ao_oracle_lcg(uint32_t* state) { return lcg(*state); }
 float ao_oracle_rnd(uint32_t* state) { return rnd(*state); }
