@@ -104,7 +104,8 @@ typedef enum AoStatus {
   AOBAKE_ERR_STATE = 3,           /* call order violated (e.g. compute before set_scene) */
   AOBAKE_ERR_SAMPLE_OVERFLOW = 4, /* area-proportional floors exceeded the budget */
   AOBAKE_ERR_NO_DEVICE = 5,
-  AOBAKE_ERR_SOLVER = 6
+  AOBAKE_ERR_SOLVER = 6,
+  AOBAKE_ERR_COMM = 7             /* NCCL missing or a collective failed */
 } AoStatus;
 
 typedef struct AoBakeParams {
@@ -191,6 +192,19 @@ int aobake_compute_ao_range(AoBake* ctx, size_t begin, size_t end, int rays_per_
  * ranges of aobake_compute_ao_range can differ by 10-15 % on a terrain). */
 int aobake_compute_ao_interleaved(AoBake* ctx, uint32_t part, uint32_t num_parts, uint32_t block_samples,
                                   int rays_per_sample, float scene_offset, float scene_maxdistance);
+/* ---- native multi-GPU exchange (NCCL, resolved at run time with dlopen("libnccl.so.2")) ----
+ * One process (or thread) per GPU.  Rank 0 calls aobake_comm_unique_id and ships the 128 bytes to
+ * the other ranks by any means; every rank then calls aobake_comm_init on its own context.
+ * aobake_compute_ao_distributed = aobake_compute_ao_interleaved(rank, nranks) + one in-place
+ * ncclAllReduce(sum) over the resident ao[] on the context's stream: afterwards every rank holds
+ * the full AO array, bit-identical to a single-GPU bake.  host_ao nullable (num_samples floats). */
+#define AOBAKE_COMM_ID_BYTES 128
+int aobake_comm_unique_id(void* id128);
+int aobake_comm_init(AoBake* ctx, int rank, int nranks, const void* id128);
+int aobake_comm_destroy(AoBake* ctx);
+int aobake_compute_ao_distributed(AoBake* ctx, int rays_per_sample, float scene_offset, float scene_maxdistance,
+                                  float* host_ao);
+
 /* Device pointer to the resident ao[num_samples] array (for an NCCL all-gather by the caller). */
 int aobake_get_ao_device(AoBake* ctx, float** d_ao, size_t* num_samples);
 /* Replace the resident AO array from the host (num_samples floats). */

@@ -28,7 +28,8 @@ _LIB = None
 EXPORTS = [
     "aobake_default_params", "aobake_create", "aobake_destroy", "aobake_last_error", "aobake_set_stream",
     "aobake_synchronize", "aobake_set_scene", "aobake_distribute_samples", "aobake_sample_instances",
-    "aobake_set_samples", "aobake_compute_ao", "aobake_compute_ao_range", "aobake_compute_ao_interleaved", "aobake_get_ao_device", "aobake_set_ao",
+    "aobake_set_samples", "aobake_compute_ao", "aobake_compute_ao_range", "aobake_compute_ao_interleaved", "aobake_comm_unique_id",
+    "aobake_comm_init", "aobake_comm_destroy", "aobake_compute_ao_distributed", "aobake_get_ao_device", "aobake_set_ao",
     "aobake_map_ao_to_vertices", "aobake_make_ground_plane", "aobake_trace_rays", "aobake_dump_rays",
     "aobake_get_hit_counts", "aobake_get_timings", "aobake_get_stats", "aobake_num_samples",
 ]
@@ -86,6 +87,10 @@ def load_library(path: Optional[str] = None):
     L.aobake_compute_ao.argtypes = [vp, i32, f32, f32, vp]
     L.aobake_compute_ao_range.argtypes = [vp, sz, sz, i32, f32, f32, vp]
     L.aobake_compute_ao_interleaved.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, i32, f32, f32]
+    L.aobake_comm_unique_id.argtypes = [vp]
+    L.aobake_comm_init.argtypes = [vp, i32, i32, vp]
+    L.aobake_comm_destroy.argtypes = [vp]
+    L.aobake_compute_ao_distributed.argtypes = [vp, i32, f32, f32, vp]
     L.aobake_get_ao_device.argtypes = [vp, C.POINTER(vp), C.POINTER(sz)]
     L.aobake_set_ao.argtypes = [vp, vp]
     L.aobake_map_ao_to_vertices.argtypes = [vp, i32, f32, vp]
@@ -209,6 +214,30 @@ class Baker:
         """Trace the super-blocks owned by `part` of `num_parts`; other samples' AO is set to 0."""
         self._ck(self.lib.aobake_compute_ao_interleaved(self._h, part, num_parts, block_samples, rays_per_sample,
                                                         float(scene_offset), float(scene_maxdistance)))
+
+    # -- native NCCL exchange (inside libaobake.so) --
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        rc = load_library().aobake_comm_unique_id(buf)
+        if rc != 0:
+            raise AoBakeError(rc, (load_library().aobake_last_error(None) or b"").decode())
+        return buf.raw
+
+    def comm_init(self, rank: int, nranks: int, unique_id: bytes):
+        assert len(unique_id) == 128
+        self._ck(self.lib.aobake_comm_init(self._h, rank, nranks, C.create_string_buffer(unique_id, 128)))
+
+    def comm_destroy(self):
+        self._ck(self.lib.aobake_comm_destroy(self._h))
+
+    def compute_ao_distributed(self, rays_per_sample: int, scene_offset: float, scene_maxdistance: float,
+                               download: bool = True) -> Optional[np.ndarray]:
+        """Interleaved partition over the ranks of comm_init + in-place ncclAllReduce, all native."""
+        ao = np.empty(self.num_samples, dtype=np.float32) if download else None
+        self._ck(self.lib.aobake_compute_ao_distributed(self._h, rays_per_sample, float(scene_offset), float(scene_maxdistance),
+                                                        ao.ctypes.data if ao is not None else None))
+        return ao
 
     def download_ao(self) -> np.ndarray:
         import ctypes as _C

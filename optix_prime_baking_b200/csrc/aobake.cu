@@ -6,6 +6,7 @@
 // CUDA device, and every compute entry point requires a live context.
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <chrono>
@@ -27,6 +28,37 @@ thread_local std::string g_create_error;
 // BVH build and the filters allocate dozens of scratch buffers, and the driver's pool makes
 // those microseconds instead of the milliseconds of cudaMalloc/cudaFree.
 thread_local cudaStream_t g_alloc_stream = nullptr;
+
+// ---- NCCL, bound at run time: no link-time dependency, and inside a process that already loaded
+// an NCCL (e.g. torch's bundled one) dlopen returns that same library ----
+struct NcclId { char internal[128]; };
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(NcclId*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  std::string error;
+  bool load() {
+    if (handle) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (handle) break;
+    }
+    if (!handle) { error = std::string("dlopen(libnccl.so.2): ") + (dlerror() ? dlerror() : "not found"); return false; }
+    GetUniqueId = reinterpret_cast<int (*)(NcclId*)>(dlsym(handle, "ncclGetUniqueId"));
+    CommInitRank = reinterpret_cast<int (*)(void**, int, NcclId, int)>(dlsym(handle, "ncclCommInitRank"));
+    CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(handle, "ncclCommDestroy"));
+    AllReduce = reinterpret_cast<int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)>(dlsym(handle, "ncclAllReduce"));
+    GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(handle, "ncclGetErrorString"));
+    if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce || !GetErrorString) { error = "libnccl lacks an expected symbol"; handle = nullptr; return false; }
+    return true;
+  }
+};
+NcclApi g_nccl;
+constexpr int kNcclFloat = 7, kNcclSum = 0;   // ncclFloat32, ncclSum
 
 template <typename T>
 struct DBuf {
@@ -138,6 +170,10 @@ struct AoBake {
   bool have_infos = false;           // sample_infos (tri_idx, bary, dA) are resident — needed by the vertex maps
 
   AoTimings timings{};
+
+  // native multi-GPU exchange
+  void* nccl_comm = nullptr;
+  int comm_rank = 0, comm_size = 1;
 
   int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -412,6 +448,7 @@ void aobake_destroy(AoBake* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->nccl_comm && g_nccl.handle) { g_nccl.CommDestroy(ctx->nccl_comm); ctx->nccl_comm = nullptr; }
   g_alloc_stream = ctx->own_stream;
   cudaStream_t own = ctx->own_stream;
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -945,6 +982,60 @@ int aobake_compute_ao_interleaved(AoBake* ctx, uint32_t part, uint32_t num_parts
   if (!ctx) return AOBAKE_ERR_INVALID_ARGUMENT;
   if (num_parts == 0) return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "num_parts must be >= 1");
   return compute_ao_impl(ctx, 0, ctx->num_samples, rays_per_sample, offset, maxdist, nullptr, part, num_parts, block_samples);
+}
+
+int aobake_comm_unique_id(void* id128) {
+  if (!id128) return AOBAKE_ERR_INVALID_ARGUMENT;
+  if (!g_nccl.load()) { g_create_error = g_nccl.error; return AOBAKE_ERR_COMM; }
+  NcclId id;
+  const int rc = g_nccl.GetUniqueId(&id);
+  if (rc != 0) { g_create_error = std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(rc); return AOBAKE_ERR_COMM; }
+  memcpy(id128, id.internal, sizeof(id.internal));
+  return AOBAKE_OK;
+}
+
+int aobake_comm_init(AoBake* ctx, int rank, int nranks, const void* id128) {
+  if (!ctx || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return AOBAKE_ERR_INVALID_ARGUMENT;
+  if (!g_nccl.load()) return ctx->fail(AOBAKE_ERR_COMM, "%s", g_nccl.error.c_str());
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->nccl_comm) { g_nccl.CommDestroy(ctx->nccl_comm); ctx->nccl_comm = nullptr; }
+  NcclId id;
+  memcpy(id.internal, id128, sizeof(id.internal));
+  const int rc = g_nccl.CommInitRank(&ctx->nccl_comm, nranks, id, rank);
+  if (rc != 0) return ctx->fail(AOBAKE_ERR_COMM, "ncclCommInitRank: %s", g_nccl.GetErrorString(rc));
+  ctx->comm_rank = rank;
+  ctx->comm_size = nranks;
+  return AOBAKE_OK;
+}
+
+int aobake_comm_destroy(AoBake* ctx) {
+  if (!ctx) return AOBAKE_ERR_INVALID_ARGUMENT;
+  if (ctx->nccl_comm && g_nccl.handle) {
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    g_nccl.CommDestroy(ctx->nccl_comm);
+  }
+  ctx->nccl_comm = nullptr;
+  ctx->comm_rank = 0;
+  ctx->comm_size = 1;
+  return AOBAKE_OK;
+}
+
+int aobake_compute_ao_distributed(AoBake* ctx, int rays_per_sample, float offset, float maxdist, float* host_ao) {
+  if (!ctx) return AOBAKE_ERR_INVALID_ARGUMENT;
+  if (ctx->comm_size > 1 && !ctx->nccl_comm) return ctx->fail(AOBAKE_ERR_STATE, "aobake_comm_init has not been called");
+  int rc = compute_ao_impl(ctx, 0, ctx->num_samples, rays_per_sample, offset, maxdist, nullptr, (uint32_t)ctx->comm_rank,
+                           (uint32_t)ctx->comm_size, 0);
+  if (rc) return rc;
+  cudaStream_t st = ctx->stream;
+  if (ctx->comm_size > 1 && ctx->num_samples) {
+    // every rank holds exact zeros outside its super-blocks: the sum assembles ao[] bit for bit
+    const int nrc = g_nccl.AllReduce(ctx->d_ao.p, ctx->d_ao.p, ctx->num_samples, kNcclFloat, kNcclSum, ctx->nccl_comm, st);
+    if (nrc != 0) return ctx->fail(AOBAKE_ERR_COMM, "ncclAllReduce: %s", g_nccl.GetErrorString(nrc));
+  }
+  if (host_ao && ctx->num_samples) CK(cudaMemcpyAsync(host_ao, ctx->d_ao.p, ctx->num_samples * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return AOBAKE_OK;
 }
 
 int aobake_compute_ao(AoBake* ctx, int rays_per_sample, float offset, float maxdist, float* host_ao) {

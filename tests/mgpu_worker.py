@@ -28,6 +28,15 @@ def main():
             ao = DistributedBaker(bk, rank, world, local).compute_ao(64, off, maxd, gather=True, download=True, interleave=True,
                                                                       block_samples=2048)
             assert np.array_equal(ao.view(np.uint32), ao_c.view(np.uint32)), 'interleaved != contiguous sharding'
+            # the same exchange done natively by libaobake.so (dlopen'd NCCL); the 128-byte id travels over torch here
+            idt = torch.zeros(128, dtype=torch.uint8, device='cuda')
+            if rank == 0:
+                idt.copy_(torch.frombuffer(bytearray(api.Baker.comm_unique_id()), dtype=torch.uint8))
+            dist.broadcast(idt, src=0)
+            bk.comm_init(rank, world, bytes(idt.cpu().numpy().tobytes()))
+            ao_native = bk.compute_ao_distributed(64, off, maxd)
+            bk.comm_destroy()
+            assert np.array_equal(ao_native.view(np.uint32), ao.view(np.uint32)), 'native NCCL exchange differs'
             v_area = bk.map_ao_to_vertices(api.FILTER_AREA_BASED)
         if rank == 0:
             with api.Baker(device=local) as ref:

@@ -69,3 +69,29 @@ def test_cpp_shim_runs(lib_path, tmp_path):
     res = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "bake_api ok" in res.stdout
+
+
+def _compile(tmp_path, src, name):
+    exe = str(tmp_path / name)
+    cmd = [GXX, "-std=c++17", "-O1", "-pthread", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", src),
+           "-o", exe, "-L", os.path.dirname(LIB), "-laobake", f"-Wl,-rpath,{os.path.dirname(LIB)}"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    return exe
+
+
+def test_cpp_distributed_compiles(lib_path, tmp_path):
+    _compile(tmp_path, "test_distributed.cpp", "test_distributed")
+
+
+@pytest.mark.gpu
+def test_cpp_distributed_runs_without_python(lib_path, tmp_path):
+    """Multi-GPU bake driven from C++ threads only: sharding + NCCL all-reduce inside libaobake.so."""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    exe = _compile(tmp_path, "test_distributed.cpp", "test_distributed")
+    res = subprocess.run([exe, str(min(n, 4))], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "distributed ok" in res.stdout
