@@ -20,7 +20,7 @@ def build_cli(tmp_path):
     from optix_prime_baking_b200 import build
     build.build()
     exe = str(tmp_path / "aobake_cli")
-    res = subprocess.run([GXX, "-std=c++17", "-O2", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tools", "aobake_cli.cpp"),
+    res = subprocess.run([GXX, "-std=c++17", "-O2", "-pthread", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tools", "aobake_cli.cpp"),
                           "-o", exe, "-L", LIBDIR, "-laobake", f"-Wl,-rpath,{LIBDIR}"], capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
     return exe
@@ -86,3 +86,20 @@ def test_cli_bake_matches_python_api(tmp_path):
     # fp64: a ray in a million may flip, moving one vertex by ~1e-3
     d = np.abs(data - want)
     assert d.max() < 5e-3 and d.mean() < 1e-5
+
+
+@pytest.mark.gpu
+def test_cli_multi_gpu_matches_single_gpu(tmp_path):
+    """--gpus 2: C++ threads + the native NCCL exchange; the AO is bit-identical, so the vertex dumps agree to fp64-atomics rounding."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    exe = build_cli(tmp_path)
+    outs = []
+    for gpus in (1, 2):
+        raw = str(tmp_path / f"g{gpus}.raw")
+        res = subprocess.run([exe, "-o", raw, "-i", "2", "-r", "64", "-s", "200000", "--no_least_squares", "--gpus", str(gpus)],
+                             capture_output=True, text=True, timeout=300)
+        assert res.returncode == 0, res.stderr
+        outs.append(read_raw(raw)[1])
+    assert np.abs(outs[0] - outs[1]).max() < 1e-6

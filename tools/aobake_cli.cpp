@@ -11,6 +11,8 @@
 //   --ray_distance d  --hit_distance d  -g/--ground_setup axis scale offset (1 100 0.03)
 //   --no_ground_plane  -w/--regularization_weight w (0.1)  --no_least_squares
 //   --flip_orientation   (--cpu is rejected: there is no CPU path)   --no_viewer accepted, ignored
+//   --gpus n (1): one host thread per GPU; the AO pass is sharded (interleaved super-blocks) and
+//                 all-reduced over NCCL inside libaobake.so, the vertex map runs on GPU 0
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -20,6 +22,7 @@
 #include <fstream>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "aobake.h"
@@ -126,13 +129,14 @@ struct Config {
   int ground_axis = 1;
   float ground_scale = 100.0f, ground_offset = 0.03f, weight = 0.1f;
   bool ground = true, least_squares = true, flip = false;
+  int gpus = 1;
 };
 
 int usage(const char* argv0) {
   fprintf(stderr,
           "usage: %s [-f scene.obj] [-o out.raw] [-i n] [-r rays] [-s samples] [-t samples_per_face]\n"
           "          [-d ray_distance_scale] [-m hit_distance_scale] [--ray_distance d] [--hit_distance d]\n"
-          "          [-g axis scale offset] [--no_ground_plane] [-w weight] [--no_least_squares] [--flip_orientation]\n",
+          "          [-g axis scale offset] [--no_ground_plane] [-w weight] [--no_least_squares] [--flip_orientation] [--gpus n]\n",
           argv0);
   return 2;
 }
@@ -162,6 +166,7 @@ int main(int argc, char** argv) {
     else if (a == "-w" || a == "--regularization_weight") cfg.weight = (float)atof(next("-w"));
     else if (a == "--no_least_squares") cfg.least_squares = false;
     else if (a == "--flip_orientation") cfg.flip = true;
+    else if (a == "--gpus") cfg.gpus = std::max(1, atoi(next("--gpus")));
     else if (a == "--no_viewer" || a == "--conserve_memory") {}
     else if (a == "--cpu") { fprintf(stderr, "--cpu: libaobake has no CPU path (B200 only)\n"); return 2; }
     else if (a == "-h" || a == "--help") return usage(argv[0]);
@@ -244,7 +249,34 @@ int main(int argc, char** argv) {
   const int q = (int)(std::sqrt((float)cfg.rays) + 0.5f);
   fprintf(stderr, "Rays per sample: %d\nTotal rays: %zu\n", q * q, total * (size_t)q * q);
   t0 = now_ms();
-  ck(aobake_compute_ao(ctx, cfg.rays, scene_offset, scene_maxdist, nullptr), "compute_ao");
+  if (cfg.gpus > 1) {
+    // helper ranks 1..n-1: same scene and samples (replicated), their share of the AO pass; rank 0 is ctx
+    char id[AOBAKE_COMM_ID_BYTES];
+    if (aobake_comm_unique_id(id) != AOBAKE_OK) { fprintf(stderr, "NCCL: %s\n", aobake_last_error(nullptr)); aobake_destroy(ctx); return 1; }
+    std::vector<int> rcs(cfg.gpus, AOBAKE_OK);
+    auto helper = [&](int rank) {
+      AoBakeParams p;
+      aobake_default_params(&p);
+      p.device = rank;
+      AoBake* c = nullptr;
+      int rc = aobake_create(&p, &c);
+      if (rc == AOBAKE_OK) rc = aobake_set_scene(c, &scene, cfg.ground ? &blockers : nullptr);
+      if (rc == AOBAKE_OK) rc = aobake_sample_instances(c, per.data(), (size_t)cfg.samples_per_face, nullptr);
+      if (rc == AOBAKE_OK) rc = aobake_comm_init(c, rank, cfg.gpus, id);
+      if (rc == AOBAKE_OK) rc = aobake_compute_ao_distributed(c, cfg.rays, scene_offset, scene_maxdist, nullptr);
+      if (rc != AOBAKE_OK) fprintf(stderr, "rank %d: %s\n", rank, c ? aobake_last_error(c) : aobake_last_error(nullptr));
+      rcs[rank] = rc;
+      if (c) aobake_destroy(c);
+    };
+    std::vector<std::thread> th;
+    for (int r = 1; r < cfg.gpus; r++) th.emplace_back(helper, r);
+    ck(aobake_comm_init(ctx, 0, cfg.gpus, id), "comm_init");
+    ck(aobake_compute_ao_distributed(ctx, cfg.rays, scene_offset, scene_maxdist, nullptr), "compute_ao_distributed");
+    for (auto& x : th) x.join();
+    for (int r = 1; r < cfg.gpus; r++) if (rcs[r] != AOBAKE_OK) { aobake_destroy(ctx); return 1; }
+  } else {
+    ck(aobake_compute_ao(ctx, cfg.rays, scene_offset, scene_maxdist, nullptr), "compute_ao");
+  }
   AoTimings tm;
   aobake_get_timings(ctx, &tm);
   fprintf(stderr, "Compute AO ... %.2f ms   (fused raygen + query + accumulate kernel %.2f ms, %.1f Mrays/s)\n", now_ms() - t0, tm.trace_ms,
