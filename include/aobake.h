@@ -204,6 +204,12 @@ int aobake_comm_init(AoBake* ctx, int rank, int nranks, const void* id128);
 int aobake_comm_destroy(AoBake* ctx);
 int aobake_compute_ao_distributed(AoBake* ctx, int rays_per_sample, float scene_offset, float scene_maxdistance,
                                   float* host_ao);
+/* bake::mapAOToVertices across the ranks of aobake_comm_init: the per-instance systems are independent
+ * (block diagonal), so each rank filters a contiguous share of the instances (balanced by vertex
+ * count) and one ncclAllReduce over zero-padded arrays gathers the result; every rank receives the
+ * vertex AO of every instance.  Requires the full AO array on every rank (compute_ao_distributed). */
+int aobake_map_ao_to_vertices_distributed(AoBake* ctx, int mode /*AoVertexFilterMode*/, float regularization_weight,
+                                          float* const* host_vertex_ao);
 
 /* Device pointer to the resident ao[num_samples] array (for an NCCL all-gather by the caller). */
 int aobake_get_ao_device(AoBake* ctx, float** d_ao, size_t* num_samples);

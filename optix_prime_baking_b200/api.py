@@ -29,7 +29,7 @@ EXPORTS = [
     "aobake_default_params", "aobake_create", "aobake_destroy", "aobake_last_error", "aobake_set_stream",
     "aobake_synchronize", "aobake_set_scene", "aobake_distribute_samples", "aobake_sample_instances",
     "aobake_set_samples", "aobake_compute_ao", "aobake_compute_ao_range", "aobake_compute_ao_interleaved", "aobake_comm_unique_id",
-    "aobake_comm_init", "aobake_comm_destroy", "aobake_compute_ao_distributed", "aobake_get_ao_device", "aobake_set_ao",
+    "aobake_comm_init", "aobake_comm_destroy", "aobake_compute_ao_distributed", "aobake_map_ao_to_vertices_distributed", "aobake_get_ao_device", "aobake_set_ao",
     "aobake_map_ao_to_vertices", "aobake_make_ground_plane", "aobake_trace_rays", "aobake_dump_rays",
     "aobake_get_hit_counts", "aobake_get_timings", "aobake_get_stats", "aobake_num_samples",
 ]
@@ -94,6 +94,7 @@ def load_library(path: Optional[str] = None):
     L.aobake_get_ao_device.argtypes = [vp, C.POINTER(vp), C.POINTER(sz)]
     L.aobake_set_ao.argtypes = [vp, vp]
     L.aobake_map_ao_to_vertices.argtypes = [vp, i32, f32, vp]
+    L.aobake_map_ao_to_vertices_distributed.argtypes = [vp, i32, f32, vp]
     L.aobake_make_ground_plane.argtypes = [vp, vp, i32, f32, f32, vp, vp]
     L.aobake_trace_rays.argtypes = [vp, vp, sz, vp]
     L.aobake_dump_rays.argtypes = [vp, sz, sz, i32, f32, f32, vp]
@@ -263,10 +264,13 @@ class Baker:
         self._ck(self.lib.aobake_get_hit_counts(self._h, out.ctypes.data))
         return out
 
-    def map_ao_to_vertices(self, mode: int = FILTER_AREA_BASED, regularization_weight: float = 0.1) -> List[np.ndarray]:
+    def map_ao_to_vertices(self, mode: int = FILTER_AREA_BASED, regularization_weight: float = 0.1,
+                           distributed: bool = False) -> List[np.ndarray]:
+        """distributed=True: split the instances over the ranks of comm_init (native NCCL gather)."""
         arrs = [np.zeros(len(self.scene.meshes[i.mesh_index].vertices), dtype=np.float32) for i in self.scene.instances]
         ptrs = (C.c_void_p * max(len(arrs), 1))(*[a.ctypes.data for a in arrs])
-        self._ck(self.lib.aobake_map_ao_to_vertices(self._h, mode, float(regularization_weight), ptrs))
+        fn = self.lib.aobake_map_ao_to_vertices_distributed if distributed else self.lib.aobake_map_ao_to_vertices
+        self._ck(fn(self._h, mode, float(regularization_weight), ptrs))
         return arrs
 
     # -- parity hooks --

@@ -1071,14 +1071,20 @@ namespace {
 
 // Global numbering shared by both vertex maps: instance i owns vertices [vbase[i], vbase[i+1]),
 // triangles, samples and (least squares) interior edges in consecutive global ranges.
-void build_filter_instances(AoBake* ctx, const std::vector<DBuf<uint32_t>>* topo, const std::vector<uint32_t>* topo_count,
-                            std::vector<LsInst>& h, std::vector<uint64_t>& vbase, uint64_t* NV, uint64_t* NT, uint64_t* NE, uint64_t* NS) {
-  const uint32_t nI = (uint32_t)ctx->insts.size();
+// The numbering is relative to the instance range [ib, ie) being solved (the whole scene, or one
+// rank's share of it: the systems are block diagonal, so instances split freely across GPUs).
+void build_filter_instances(AoBake* ctx, uint32_t ib, uint32_t ie, const std::vector<DBuf<uint32_t>>* topo,
+                            const std::vector<uint32_t>* topo_count, std::vector<LsInst>& h, std::vector<uint64_t>& vbase, uint64_t* NV,
+                            uint64_t* NT, uint64_t* NE, uint64_t* NS, uint64_t* sample0) {
+  const uint32_t nI = ie - ib;
   h.assign(std::max(nI, 1u), LsInst{});
   vbase.assign(nI + 1, 0);
+  uint64_t s0 = 0;
+  for (uint32_t i = 0; i < ib; i++) s0 += ctx->per_instance[i];
+  *sample0 = s0;
   uint64_t nv = 0, nt = 0, ne = 0, ns = 0;
   for (uint32_t i = 0; i < nI; i++) {
-    const HostInstance& I = ctx->insts[i];
+    const HostInstance& I = ctx->insts[ib + i];
     const DeviceMesh& M = ctx->meshes[I.mesh];
     LsInst& L = h[i];
     memcpy(L.xf, I.xf, sizeof(L.xf));
@@ -1086,53 +1092,48 @@ void build_filter_instances(AoBake* ctx, const std::vector<DBuf<uint32_t>>* topo
     L.sample_begin = ns; L.tri_begin = nt; L.edge_begin = ne; L.vert_begin = (uint32_t)nv;
     L.num_tris = (uint32_t)M.nT; L.num_edges = topo_count ? (*topo_count)[I.mesh] : 0u; L.pad = 0;
     vbase[i] = nv;
-    ns += ctx->per_instance[i]; nt += M.nT; ne += L.num_edges; nv += M.nV;
+    ns += ctx->per_instance[ib + i]; nt += M.nT; ne += L.num_edges; nv += M.nV;
   }
   vbase[nI] = nv;
   *NV = nv; *NT = nt; *NE = ne; *NS = ns;
 }
 
 // bake_filter.cpp filter / filter_mesh for all instances in one pass.
-int area_filter_batched(AoBake* ctx, float* const* host_vertex_ao) {
+int area_filter_batched(AoBake* ctx, uint32_t ib, uint32_t ie, DBuf<float>& d_out) {
   cudaStream_t st = ctx->stream;
-  const uint32_t nI = (uint32_t)ctx->insts.size();
+  const uint32_t nI = ie - ib;
   std::vector<LsInst> h;
   std::vector<uint64_t> vbase;
-  uint64_t NV = 0, NT = 0, NE = 0, NS = 0;
-  build_filter_instances(ctx, nullptr, nullptr, h, vbase, &NV, &NT, &NE, &NS);
+  uint64_t NV = 0, NT = 0, NE = 0, NS = 0, S0 = 0;
+  build_filter_instances(ctx, ib, ie, nullptr, nullptr, h, vbase, &NV, &NT, &NE, &NS, &S0);
   if (NV > 0xfffffff0ull) return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "too many vertices for 32-bit indices");
-  if (NS != ctx->num_samples) return ctx->fail(AOBAKE_ERR_STATE, "per-instance sample counts do not add up to the resident samples");
+  if (S0 + NS > ctx->num_samples) return ctx->fail(AOBAKE_ERR_STATE, "per-instance sample counts exceed the resident samples");
   const uint64_t v1 = std::max<uint64_t>(NV, 1);
   DBuf<LsInst> d_inst;
   DBuf<double> num, wgt;
-  DBuf<float> d_out;
   CK(d_inst.alloc(std::max(nI, 1u))); CK(num.alloc(v1)); CK(wgt.alloc(v1)); CK(d_out.alloc(v1));
   if (nI) CK(cudaMemcpyAsync(d_inst.p, h.data(), nI * sizeof(LsInst), cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(num.p, 0, v1 * sizeof(double), st));
   CK(cudaMemsetAsync(wgt.p, 0, v1 * sizeof(double), st));
-  if (NS) k_area_scatter_b<<<grid_for(NS, 256), 256, 0, st>>>(ctx->d_info.p, ctx->d_ao.p, NS, d_inst.p, nI, num.p, wgt.p);
+  if (NS) k_area_scatter_b<<<grid_for(NS, 256), 256, 0, st>>>(ctx->d_info.p + S0, ctx->d_ao.p + S0, NS, d_inst.p, nI, num.p, wgt.p);
   if (NV) k_area_final<<<grid_for(NV, 256), 256, 0, st>>>(num.p, wgt.p, NV, d_out.p);
   CKL();
-  for (uint32_t i = 0; i < nI; i++) {
-    const uint64_t nv = vbase[i + 1] - vbase[i];
-    if (nv && host_vertex_ao[i]) CK(cudaMemcpyAsync(host_vertex_ao[i], d_out.p + vbase[i], nv * sizeof(float), cudaMemcpyDeviceToHost, st));
-  }
   CK(cudaStreamSynchronize(st));
   return AOBAKE_OK;
 }
 
 // bake_filter_least_squares.cpp: (M + w R) x = b, fp64, for ALL instances as one block-diagonal
 // system, matrix-free Jacobi-PCG.
-int ls_filter_batched(AoBake* ctx, float weight, float* const* host_vertex_ao) {
+int ls_filter_batched(AoBake* ctx, float weight, uint32_t ib, uint32_t ie, DBuf<float>& d_out) {
   cudaStream_t st = ctx->stream;
-  const uint32_t nI = (uint32_t)ctx->insts.size();
+  const uint32_t nI = ie - ib;
   const double w = weight;
   // ---- interior-edge topology, once per mesh that is instanced ----
   const size_t nM = ctx->meshes.size();
   std::vector<DBuf<uint32_t>> topo(nM);
   std::vector<uint32_t> topo_count(nM, 0);
   std::vector<char> used(nM, 0);
-  for (const HostInstance& I : ctx->insts) used[I.mesh] = 1;
+  for (uint32_t i = ib; i < ie; i++) used[ctx->insts[i].mesh] = 1;
   if (weight != 0.0f) {
     for (size_t m = 0; m < nM; m++) {
       const DeviceMesh& M = ctx->meshes[m];
@@ -1159,17 +1160,16 @@ int ls_filter_batched(AoBake* ctx, float weight, float* const* host_vertex_ao) {
   // ---- instance descriptors and global numbering ----
   std::vector<LsInst> h;
   std::vector<uint64_t> vbase;
-  uint64_t NV = 0, NT = 0, NE = 0, NS = 0;
-  build_filter_instances(ctx, &topo, &topo_count, h, vbase, &NV, &NT, &NE, &NS);
+  uint64_t NV = 0, NT = 0, NE = 0, NS = 0, S0 = 0;
+  build_filter_instances(ctx, ib, ie, &topo, &topo_count, h, vbase, &NV, &NT, &NE, &NS, &S0);
   if (NV > 0xfffffff0ull || NE > 0xfffffff0ull) return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "least-squares system too large for 32-bit indices");
-  if (NS != ctx->num_samples) return ctx->fail(AOBAKE_ERR_STATE, "per-instance sample counts do not add up to the resident samples");
+  if (S0 + NS > ctx->num_samples) return ctx->fail(AOBAKE_ERR_STATE, "per-instance sample counts exceed the resident samples");
   const uint64_t v1 = std::max<uint64_t>(NV, 1), t1 = std::max<uint64_t>(NT, 1);
   DBuf<LsInst> d_inst;
   DBuf<uint32_t> gtris;
   DBuf<double> Mt, rhs, diag, x, r, z, p, Ap, scal;
   DBuf<uint8_t> fixed;
   DBuf<LsEdge> edges;
-  DBuf<float> d_out;
   CK(d_inst.alloc(std::max(nI, 1u))); CK(gtris.alloc(3 * t1)); CK(Mt.alloc(6 * t1)); CK(rhs.alloc(v1)); CK(diag.alloc(v1));
   CK(x.alloc(v1)); CK(r.alloc(v1)); CK(z.alloc(v1)); CK(p.alloc(v1)); CK(Ap.alloc(v1)); CK(scal.alloc(8)); CK(fixed.alloc(v1));
   CK(edges.alloc(std::max<uint64_t>(NE, 1))); CK(d_out.alloc(v1));
@@ -1178,7 +1178,7 @@ int ls_filter_batched(AoBake* ctx, float weight, float* const* host_vertex_ao) {
   CK(cudaMemsetAsync(rhs.p, 0, v1 * sizeof(double), st));
   CK(cudaMemsetAsync(diag.p, 0, v1 * sizeof(double), st));
   if (NT) k_ls_gtris<<<grid_for(NT, 256), 256, 0, st>>>(d_inst.p, nI, NT, gtris.p);
-  if (NS) k_ls_mass_b<<<grid_for(NS, 256), 256, 0, st>>>(ctx->d_info.p, ctx->d_ao.p, NS, d_inst.p, nI, gtris.p, Mt.p, rhs.p);
+  if (NS) k_ls_mass_b<<<grid_for(NS, 256), 256, 0, st>>>(ctx->d_info.p + S0, ctx->d_ao.p + S0, NS, d_inst.p, nI, gtris.p, Mt.p, rhs.p);
   if (NE) k_ls_edge_coeffs<<<grid_for(NE, 256), 256, 0, st>>>(d_inst.p, nI, NE, edges.p);
   if (NT) k_ls_diag_mass<<<grid_for(NT, 256), 256, 0, st>>>(gtris.p, NT, Mt.p, diag.p);
   if (NV) k_ls_fix<<<grid_for(NV, 256), 256, 0, st>>>(diag.p, rhs.p, fixed.p, NV);
@@ -1225,10 +1225,6 @@ int ls_filter_batched(AoBake* ctx, float weight, float* const* host_vertex_ao) {
   ctx->timings.cg_iterations = it;
   if (NV) k_d2f<<<grid_for(NV, 256), 256, 0, st>>>(x.p, d_out.p, NV);
   CKL();
-  for (uint32_t i = 0; i < nI; i++) {
-    const uint64_t nv = vbase[i + 1] - vbase[i];
-    if (nv && host_vertex_ao[i]) CK(cudaMemcpyAsync(host_vertex_ao[i], d_out.p + vbase[i], nv * sizeof(float), cudaMemcpyDeviceToHost, st));
-  }
   CK(cudaStreamSynchronize(st));
   return AOBAKE_OK;
 }
@@ -1237,28 +1233,68 @@ int ls_filter_batched(AoBake* ctx, float weight, float* const* host_vertex_ao) {
 
 extern "C" {
 
-int aobake_map_ao_to_vertices(AoBake* ctx, int mode, float weight, float* const* host_vertex_ao) {
+static int map_ao_impl(AoBake* ctx, int mode, float weight, float* const* host_vertex_ao, bool distributed) {
   if (!ctx || !host_vertex_ao) return AOBAKE_ERR_INVALID_ARGUMENT;
   if (!ctx->have_scene || !ctx->have_ao) return ctx->fail(AOBAKE_ERR_STATE, "map_ao_to_vertices needs a scene and AO values");
   if (ctx->per_instance.size() != ctx->insts.size()) return ctx->fail(AOBAKE_ERR_STATE, "per-instance sample counts unknown (pass them to set_samples)");
   if (ctx->num_samples && !ctx->have_infos) return ctx->fail(AOBAKE_ERR_STATE, "sample_infos were not uploaded (set_samples was given a null sample_infos)");
   if (mode != AOBAKE_FILTER_AREA_BASED && mode != AOBAKE_FILTER_LEAST_SQUARES) return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "invalid filter mode %d", mode);
+  const bool dist = distributed && ctx->comm_size > 1;
+  if (dist && !ctx->nccl_comm) return ctx->fail(AOBAKE_ERR_STATE, "aobake_comm_init has not been called");
   ScopedTimer tm(ctx);
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   CK(cudaEventRecord(ctx->ev0, st));
   ctx->timings.cg_iterations = 0;
-  if (mode == AOBAKE_FILTER_LEAST_SQUARES) {
-    const int rc = ls_filter_batched(ctx, weight, host_vertex_ao);
-    if (rc) return rc;
-  } else {
-    const int rc = area_filter_batched(ctx, host_vertex_ao);
-    if (rc) return rc;
+  const uint32_t nI = (uint32_t)ctx->insts.size();
+  // global vertex offsets of all instances
+  std::vector<uint64_t> vb(nI + 1, 0);
+  for (uint32_t i = 0; i < nI; i++) vb[i + 1] = vb[i] + ctx->meshes[ctx->insts[i].mesh].nV;
+  const uint64_t NVall = vb[nI];
+  // this rank's contiguous share of the instances, balanced by vertex count
+  uint32_t ib = 0, ie = nI;
+  if (dist) {
+    auto cut = [&](int r) -> uint32_t {
+      const uint64_t target = NVall * (uint64_t)r / (uint64_t)ctx->comm_size;
+      return (uint32_t)(std::lower_bound(vb.begin(), vb.end(), target) - vb.begin());
+    };
+    ib = std::min(cut(ctx->comm_rank), nI);
+    ie = ctx->comm_rank + 1 == ctx->comm_size ? nI : std::min(cut(ctx->comm_rank + 1), nI);
+    if (ie < ib) ie = ib;
+  }
+  DBuf<float> d_sub;
+  int rc = mode == AOBAKE_FILTER_LEAST_SQUARES ? ls_filter_batched(ctx, weight, ib, ie, d_sub) : area_filter_batched(ctx, ib, ie, d_sub);
+  if (rc) return rc;
+  const float* d_all = d_sub.p;   // vertex AO of every instance, global numbering
+  DBuf<float> d_full;
+  if (dist) {
+    // block-diagonal systems: every rank solved its own instances; zeros elsewhere + sum = gather
+    CK(d_full.alloc(std::max<uint64_t>(NVall, 1)));
+    CK(cudaMemsetAsync(d_full.p, 0, std::max<uint64_t>(NVall, 1) * sizeof(float), st));
+    const uint64_t nsub = vb[ie] - vb[ib];
+    if (nsub) CK(cudaMemcpyAsync(d_full.p + vb[ib], d_sub.p, nsub * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (NVall) {
+      const int nrc = g_nccl.AllReduce(d_full.p, d_full.p, NVall, kNcclFloat, kNcclSum, ctx->nccl_comm, st);
+      if (nrc != 0) return ctx->fail(AOBAKE_ERR_COMM, "ncclAllReduce: %s", g_nccl.GetErrorString(nrc));
+    }
+    d_all = d_full.p;
+  }
+  for (uint32_t i = 0; i < nI; i++) {
+    const uint64_t nv = vb[i + 1] - vb[i];
+    if (nv && host_vertex_ao[i]) CK(cudaMemcpyAsync(host_vertex_ao[i], d_all + vb[i], nv * sizeof(float), cudaMemcpyDeviceToHost, st));
   }
   CK(cudaEventRecord(ctx->ev1, st));
   CK(cudaStreamSynchronize(st));
   CK(cudaEventElapsedTime(&ctx->timings.filter_ms, ctx->ev0, ctx->ev1));
   return AOBAKE_OK;
+}
+
+int aobake_map_ao_to_vertices(AoBake* ctx, int mode, float weight, float* const* host_vertex_ao) {
+  return map_ao_impl(ctx, mode, weight, host_vertex_ao, false);
+}
+
+int aobake_map_ao_to_vertices_distributed(AoBake* ctx, int mode, float weight, float* const* host_vertex_ao) {
+  return map_ao_impl(ctx, mode, weight, host_vertex_ao, true);
 }
 
 int aobake_make_ground_plane(const float bbox_min[3], const float bbox_max[3], int upaxis, float scale_factor, float offset_factor,

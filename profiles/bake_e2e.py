@@ -44,10 +44,19 @@ for rep in range(2):
         total, per = bk.distribute_samples(min_per, requested)
         bk.sample_instances(per, min_per, download=False)
         t2 = time.perf_counter()
-        DistributedBaker(bk, rank, world, local).compute_ao(rays, off, maxd, gather=True)
+        if world > 1:
+            # native path: sharding, NCCL all-reduce of ao[] and the instance-split vertex map all inside libaobake.so
+            idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                idt.copy_(torch.frombuffer(bytearray(api.Baker.comm_unique_id()), dtype=torch.uint8))
+            dist.broadcast(idt, src=0)
+            bk.comm_init(rank, world, idt.cpu().numpy().tobytes())
+            bk.compute_ao_distributed(rays, off, maxd, download=False)
+        else:
+            bk.compute_ao(rays, off, maxd, download=False)
         t3 = time.perf_counter()
         trace_ms = bk.timings().trace_ms
-        v = bk.map_ao_to_vertices(api.FILTER_LEAST_SQUARES if mode == "ls" else api.FILTER_AREA_BASED, 0.1)
+        v = bk.map_ao_to_vertices(api.FILTER_LEAST_SQUARES if mode == "ls" else api.FILTER_AREA_BASED, 0.1, distributed=world > 1)
         t4 = time.perf_counter()
         tf = bk.timings()
         st = bk.stats()

@@ -35,9 +35,16 @@ def main():
             dist.broadcast(idt, src=0)
             bk.comm_init(rank, world, bytes(idt.cpu().numpy().tobytes()))
             ao_native = bk.compute_ao_distributed(64, off, maxd)
+            v_dist = bk.map_ao_to_vertices(api.FILTER_LEAST_SQUARES, 0.1, distributed=True)   # instances split over the ranks
+            v_repl = bk.map_ao_to_vertices(api.FILTER_LEAST_SQUARES, 0.1)
+            for a, b in zip(v_dist, v_repl):
+                assert np.abs(a - b).max() < 1e-4, 'distributed vertex map differs from the replicated one'
+            va_dist = bk.map_ao_to_vertices(api.FILTER_AREA_BASED, distributed=True)
             bk.comm_destroy()
             assert np.array_equal(ao_native.view(np.uint32), ao.view(np.uint32)), 'native NCCL exchange differs'
             v_area = bk.map_ao_to_vertices(api.FILTER_AREA_BASED)
+            for a, b in zip(va_dist, v_area):
+                assert np.abs(a - b).max() < 1e-6
         if rank == 0:
             with api.Baker(device=local) as ref:
                 ref.set_scene(scene, blockers)
