@@ -95,3 +95,24 @@ def test_cpp_distributed_runs_without_python(lib_path, tmp_path):
     res = subprocess.run([exe, str(min(n, 4))], capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "distributed ok" in res.stdout
+
+
+def test_ctypes_mirrors_match_the_c_compiler(tmp_path):
+    """sizeof/offsetof of every struct in aobake.h as gcc sees them == the ctypes mirrors."""
+    import ctypes as C
+    from optix_prime_baking_b200 import api
+    from optix_prime_baking_b200 import ctypes_types as ct
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "aobake.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+                   'sizeof(AoMesh),offsetof(AoMesh,num_triangles),offsetof(AoMesh,bbox_min),sizeof(AoInstance),offsetof(AoInstance,storage_identifier),'
+                   'offsetof(AoInstance,mesh_index),sizeof(AoScene),sizeof(AoSampleInfo),sizeof(AoSamples),sizeof(AoBakeParams),offsetof(AoBakeParams,refill_below),'
+                   'sizeof(AoTimings),offsetof(AoTimings,rays_traced),sizeof(AoStats));return 0;}\n')
+    exe = str(tmp_path / "layout")
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    assert subprocess.run([gcc, "-I", os.path.join(ROOT, "include"), str(src), "-o", exe], capture_output=True).returncode == 0
+    got = [int(x) for x in subprocess.run([exe], capture_output=True, text=True).stdout.split()]
+    want = [C.sizeof(ct.AoMesh), ct.AoMesh.num_triangles.offset, ct.AoMesh.bbox_min.offset, C.sizeof(ct.AoInstance),
+            ct.AoInstance.storage_identifier.offset, ct.AoInstance.mesh_index.offset, C.sizeof(ct.AoScene), C.sizeof(ct.AoSampleInfo),
+            C.sizeof(ct.AoSamples), C.sizeof(api.AoBakeParams), api.AoBakeParams.refill_below.offset, C.sizeof(api.AoTimings),
+            api.AoTimings.rays_traced.offset, C.sizeof(api.AoStats)]
+    assert got == want
