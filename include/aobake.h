@@ -116,7 +116,8 @@ typedef struct AoBakeParams {
   int32_t trace_kernel;           /* 0 = auto (persistent refilling kernel; simple kernel below 32 M rays); 1 = simple; 2 = persistent */
   int32_t collect_stats;          /* 1: count node visits / triangle tests in aobake_compute_ao */
   int32_t refill_below;           /* persistent kernel: refill a warp when fewer lanes are traversing (0 = default 28) */
-  int32_t reserved[7];
+  int32_t leaf_tris;              /* triangles per leaf slot of the 8-wide BVH, 1..3 (0 = default: 2 flattened, 1 per BLAS) */
+  int32_t reserved[6];
 } AoBakeParams;
 
 typedef struct AoTimings {        /* milliseconds, device-timed with CUDA events unless noted */

@@ -396,6 +396,7 @@ int aobake_default_params(AoBakeParams* p) {
   p->trace_kernel = 0;
   p->collect_stats = 0;
   p->refill_below = 0;
+  p->leaf_tris = 0;
   return AOBAKE_OK;
 }
 
@@ -526,6 +527,11 @@ int aobake_set_scene(AoBake* ctx, const AoScene* scene, const AoScene* blockers)
   ctx->two_level = two_level;
 
   // ---- BVH build ----
+  // Triangles per leaf slot.  Fewer triangles per leaf = more nodes but fewer triangle tests, and a
+  // triangle test costs a warp far more than a node test because so few lanes are in one at a time.
+  // Measured (profiles/r1/sweep_leaf_tris.log): 2 is best for flattened scenes (config 2 +1.9 %,
+  // config 3 +2.8 % over 3); 1 is best for a BLAS, which is small and cache resident (config 4 +13.6 %).
+  const uint32_t leaf_tris = (ctx->params.leaf_tris >= 1 && ctx->params.leaf_tris <= 3) ? (uint32_t)ctx->params.leaf_tris : (two_level ? 1u : 2u);
   CK(cudaEventRecord(ctx->ev0, st));
   struct Ref { const DeviceMesh* mesh; const HostInstance* inst; };
   std::vector<Ref> all;
@@ -554,7 +560,7 @@ int aobake_set_scene(AoBake* ctx, const AoScene* scene, const AoScene* blockers)
     }
     CKL();
     Segment seg;
-    if ((rc = build_segment(ctx, plo.p, phi.p, n, 3, 0, 0, nodes.p, leaf_prims.p, &seg))) return rc;
+    if ((rc = build_segment(ctx, plo.p, phi.p, n, leaf_tris, 0, 0, nodes.p, leaf_prims.p, &seg))) return rc;
     // every visited node pushes at most one stack entry: the stack never holds more than the tree depth
     if (seg.levels + 2 > kStackSize)
       return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "BVH depth %d exceeds the traversal stack (%d entries)", seg.levels, kStackSize);
@@ -595,7 +601,7 @@ int aobake_set_scene(AoBake* ctx, const AoScene* scene, const AoScene* blockers)
       memset(&idn, 0, sizeof(idn));
       if (n) k_make_tris<<<grid_for(n, 256), 256, 0, st>>>(m->verts.p, m->tris.p, n, idn, 1, 0, soup.p, plo.p, phi.p);
       CKL();
-      if ((rc = build_segment(ctx, plo.p, phi.p, n, 3, node_off, prim_off, nodes.p, leaf_prims.p, &segs[mi]))) return rc;
+      if ((rc = build_segment(ctx, plo.p, phi.p, n, leaf_tris, node_off, prim_off, nodes.p, leaf_prims.p, &segs[mi]))) return rc;
       if (n) k_gather_tris<<<grid_for(n, 256), 256, 0, st>>>(soup.p, leaf_prims.p, n, 0, ctx->d_tris.p + 3ull * prim_off);
       CKL();
       CK(cudaStreamSynchronize(st));

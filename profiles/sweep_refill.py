@@ -6,8 +6,8 @@ import bench
 scene, blockers, min_per, requested, desc = bench.make_workload(w)
 rays=bench.RAYS[w]
 off,maxd=scenes.default_distances(scene)
-for tk, rb in [(2,30)]:
-    with api.Baker(trace_kernel=tk, refill_below=rb) as bk:
+for tk, rb, lt in [(2,30,0)]:
+    with api.Baker(trace_kernel=tk, refill_below=rb, leaf_tris=lt) as bk:
         bk.set_scene(scene, blockers)
         total, per = bk.distribute_samples(min_per, requested)
         bk.sample_instances(per, min_per, download=False)
@@ -17,4 +17,4 @@ for tk, rb in [(2,30)]:
             bk.compute_ao(rays, off, maxd, download=False, begin=0, end=n)
             ts.append(bk.timings().trace_ms)
         t=min(ts); q2=int(round(rays**0.5))**2
-        print(w, "kernel",tk,"refill_below",rb, "ms %.2f"%t, "Grays/s %.2f"%(n*q2/t/1e6), flush=True)
+        print(w, "kernel",tk,"refill_below",rb,"leaf_tris",lt, "ms %.2f"%t, "Grays/s %.2f"%(n*q2/t/1e6), flush=True)

@@ -13,6 +13,8 @@
 
 using namespace aob;
 
+static uint32_t g_max_leaf_override = 0;   // experiments: leaf slot capacity (0 = builder default)
+
 struct EmuBvh {
   std::vector<Node8> nodes;
   std::vector<F4> tris;
@@ -67,7 +69,7 @@ static uint32_t build_segment(const std::vector<F4>& plo, const std::vector<F4>&
   CollapseArgs A;
   A.L = L; A.nodes = nodes.data(); A.wide2bin = wide2bin.data(); A.leaf_prims = leaf_prims.data();
   A.node_count = &node_count; A.prim_count = &prim_count; A.node_offset = node_offset; A.prim_offset = prim_offset;
-  A.max_leaf = max_leaf;
+  A.max_leaf = (g_max_leaf_override && max_leaf > 1) ? g_max_leaf_override : max_leaf;
   wide2bin[0] = root_ref;
   uint32_t lb = 0, le = 1;
   while (lb < le) {
@@ -175,6 +177,7 @@ void* emu_bvh_create_two_level(uint32_t num_meshes, const float* const* mesh_tri
   return B;
 }
 
+void emu_set_max_leaf(uint32_t m) { g_max_leaf_override = m; }
 void emu_bvh_destroy(void* h) { delete static_cast<EmuBvh*>(h); }
 uint64_t emu_bvh_num_nodes(void* h) { return static_cast<EmuBvh*>(h)->nodes.size(); }
 
