@@ -349,3 +349,36 @@ def test_interleaved_parts_sum_to_full_bake(api, name, parts, block):
             acc += part
         assert rays == total * 64 and np.all(owned == 1)
         assert np.array_equal(acc.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("scale,offset,seed", [(1.0, 0.0, 1), (1e-3, 0.0, 2), (1e3, 0.0, 3), (1.0, 5e3, 4), (0.05, -2e4, 5)])
+def test_fuzz_triangle_soups_match_brute_force(api, scale, offset, seed):
+    """Random triangle soups (slivers, tiny and huge triangles, scenes far from the origin) and random
+    rays (axis-parallel, origins on triangles): the GPU traversal equals the oracle's brute force."""
+    rng = np.random.default_rng(seed)
+    n, m = 3000, 40000
+    c = rng.uniform(-1, 1, (n, 1, 3)) * scale
+    size = (10.0 ** rng.uniform(-3, 0, (n, 1, 1))) * scale
+    tri = c + rng.normal(size=(n, 3, 3)) * size
+    tri[: n // 10, 2] = tri[: n // 10, 0] + (tri[: n // 10, 1] - tri[: n // 10, 0]) * rng.uniform(0.4, 0.6, (n // 10, 1)) \
+        + rng.normal(size=(n // 10, 3)) * size[: n // 10, 0] * 1e-4
+    tri = np.ascontiguousarray((tri + offset).reshape(n, 9), dtype=np.float32)
+    rays = np.zeros((m, 8), dtype=np.float32)
+    rays[:, 0:3] = rng.uniform(-1.5, 1.5, (m, 3)) * scale + offset
+    d = rng.normal(size=(m, 3))
+    d[: m // 20, rng.integers(0, 3)] = 0.0
+    d[m // 20: m // 10] = np.eye(3)[rng.integers(0, 3, m // 10 - m // 20)] * rng.choice([-1.0, 1.0], (m // 10 - m // 20, 1))
+    rays[:, 4:7] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    k = m // 10
+    pick = rng.integers(0, n, k)
+    b = rng.dirichlet([1, 1, 1], k).astype(np.float32)
+    rays[-k:, 0:3] = (tri[pick].reshape(k, 3, 3) * b[:, :, None]).sum(axis=1)
+    rays[:, 7] = rng.uniform(0.1, 4.0, m).astype(np.float32) * scale
+    mesh = Mesh(tri.reshape(-1, 3), np.arange(3 * n, dtype=np.uint32).reshape(n, 3))
+    scene = Scene([mesh], [Instance(0)])
+    want = Oracle(scene).trace_rays(rays, brute=True)
+    with api.Baker() as bk:
+        bk.set_scene(scene)
+        got = bk.trace_rays(rays)
+    assert 0.01 < want.mean() < 0.99
+    assert np.array_equal(got, want)

@@ -255,3 +255,43 @@ def test_woop_variants_agree_bit_for_bit(emu):
     wt = _world_tris([sc, bl])
     rays = _random_rays(sc, 2000, 9)
     assert emu.emu_woop_variants_agree(rays.ctypes.data, len(rays), wt.ctypes.data, len(wt)) == 0
+
+
+@pytest.mark.parametrize("scale,offset,seed", [(1.0, 0.0, 1), (1e-3, 0.0, 2), (1e3, 0.0, 3), (1.0, 5e3, 4), (0.05, -2e4, 5), (1.0, 0.0, 6)])
+def test_fuzz_quantised_traversal_is_conservative(emu, scale, offset, seed):
+    """Random triangle soups (sliver, tiny and huge triangles, scenes far from the origin) and random
+    rays (including axis-parallel ones and origins on triangle planes): the emulated 8-wide quantised
+    traversal must report exactly the brute-force any-hit answer — a box culled by rounding would
+    show up as a false miss."""
+    rng = np.random.default_rng(seed)
+    n = 3000
+    c = rng.uniform(-1, 1, (n, 1, 3)) * scale
+    size = (10.0 ** rng.uniform(-3, 0, (n, 1, 1))) * scale
+    tri = c + rng.normal(size=(n, 3, 3)) * size
+    tri[: n // 10, 2] = tri[: n // 10, 0] + (tri[: n // 10, 1] - tri[: n // 10, 0]) * rng.uniform(0.4, 0.6, (n // 10, 1)) \
+        + rng.normal(size=(n // 10, 3)) * size[: n // 10, 0] * 1e-4                      # slivers
+    tri = np.ascontiguousarray((tri + offset).reshape(n, 9), dtype=np.float32)
+    m = 20000
+    rays = np.zeros((m, 8), dtype=np.float32)
+    rays[:, 0:3] = rng.uniform(-1.5, 1.5, (m, 3)) * scale + offset
+    d = rng.normal(size=(m, 3))
+    d[: m // 20, rng.integers(0, 3)] = 0.0                                                 # axis-parallel components
+    d[m // 20: m // 10] = np.eye(3)[rng.integers(0, 3, m // 10 - m // 20)] * rng.choice([-1.0, 1.0], (m // 10 - m // 20, 1))
+    rays[:, 4:7] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    # a tenth of the rays start on a triangle (t = 0 exactly at the origin's own triangle)
+    k = m // 10
+    pick = rng.integers(0, n, k)
+    b = rng.dirichlet([1, 1, 1], k).astype(np.float32)
+    rays[-k:, 0:3] = (tri[pick].reshape(k, 3, 3) * b[:, :, None]).sum(axis=1)
+    rays[:, 7] = rng.uniform(0.1, 4.0, m).astype(np.float32) * scale
+    from optix_prime_baking_b200.scenes import Instance, Mesh, Scene
+    mesh = Mesh(tri.reshape(-1, 3), np.arange(3 * n, dtype=np.uint32).reshape(n, 3))
+    orc = Oracle(Scene([mesh], [Instance(0)]))
+    want = orc.trace_rays(rays, brute=True)
+    assert np.array_equal(orc.trace_rays(rays), want)                                      # the oracle's own BVH
+    B = emu.emu_bvh_create_flat(tri.ctypes.data, n)
+    hit = np.zeros(m, dtype=np.uint8)
+    emu.emu_trace(B, rays.ctypes.data, m, hit.ctypes.data, None)
+    emu.emu_bvh_destroy(B)
+    assert 0.01 < want.mean() < 0.99
+    assert np.array_equal(hit, want)
