@@ -421,11 +421,19 @@ __global__ void __launch_bounds__(256) k_ao_simple(BvhView bvh, SampleView S, ui
 //   * lanes whose ray terminates go idle; when fewer than `refill_below` lanes of the warp are
 //     still traversing, the idle lanes generate their next rays together (so ray generation
 //     runs converged) and traversal resumes — the warp-level compaction/refill of north_star;
-//   * the traversal stack lives in shared memory ([depth][thread], conflict-free 8-byte
-//     columns) for the first kSmStack entries and spills to local memory beyond;
+//   * the traversal stack is a per-thread local-memory array (L1 resident); a shared-memory head
+//     ([depth][thread] columns, AOB_SM_STACK entries) is available but measured slower;
 //   * the Woop shear constants are computed lazily, only by lanes that reach a triangle.
 constexpr int kAoBlock = 128;
-constexpr int kSmStack = 6;
+// Entries of the traversal stack kept in shared memory ([depth][thread] columns); the rest lives in
+// local memory.  Measured on B200 (profiles/r1/sweep_stack_placement.log): 0 — the whole stack in
+// L1-resident local memory — is fastest (config 2: 12.87 vs 12.24 Grays/s with 6, config 3: 7.13 vs
+// 6.88): AO rays push and pop rarely, the shared variant pays index arithmetic and a branch per
+// access, and every KB of shared memory is a KB less L1 for BVH nodes.
+#ifndef AOB_SM_STACK
+#define AOB_SM_STACK 0
+#endif
+constexpr int kSmStack = AOB_SM_STACK;
 
 template <bool STATS, bool TWO_LEVEL, bool CLAMP_TMAX>
 __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleView S, uint64_t begin, uint32_t n, int q, float offset,
@@ -433,19 +441,29 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
                                                              uint32_t part, uint32_t num_parts, uint32_t sb_blocks, uint32_t n_local_blocks,
                                                              uint32_t* __restrict__ hits, unsigned long long* __restrict__ counter,
                                                              unsigned long long* __restrict__ stats) {
+#if AOB_SM_STACK > 0
   __shared__ U2 s_stack[kSmStack][kAoBlock];
+#endif
   U2 l_stack[kStackSize - kSmStack];
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t lt_mask = (1u << lane) - 1u;
   const uint32_t q2 = (uint32_t)(q * q);
   auto push = [&](int& sp, U2 v) {
+#if AOB_SM_STACK > 0
     if (sp < kSmStack) s_stack[sp][threadIdx.x] = v;
     else l_stack[sp - kSmStack] = v;
+#else
+    l_stack[sp] = v;
+#endif
     sp++;
   };
   auto pop = [&](int& sp) -> U2 {
     sp--;
+#if AOB_SM_STACK > 0
     return sp < kSmStack ? s_stack[sp][threadIdx.x] : l_stack[sp - kSmStack];
+#else
+    return l_stack[sp];
+#endif
   };
 
   const NodeConsts nc = make_node_consts();
