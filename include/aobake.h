@@ -161,7 +161,10 @@ int aobake_synchronize(AoBake* ctx);
 
 /* ---- the bake path ---------------------------------------------------------------- */
 /* Uploads scene + blockers (nullable) and builds the BVH (bake_ao_optix_prime.cpp:
- * rtpModelSetTriangles/SetInstances/Update). */
+ * rtpModelSetTriangles/SetInstances/Update).  The reference asserts on bad input; here a
+ * mesh index out of range, a triangle index >= num_vertices, or a singular / non-finite
+ * instance transform returns AOBAKE_ERR_INVALID_ARGUMENT and leaves the context without a
+ * scene.  Only the affine 3x4 part of xform is used (the fourth row is ignored). */
 int aobake_set_scene(AoBake* ctx, const AoScene* scene, const AoScene* blockers);
 
 /* bake::distributeSamples.  per_instance has scene->num_instances entries. */

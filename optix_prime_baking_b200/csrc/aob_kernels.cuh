@@ -170,6 +170,12 @@ __global__ void k_collapse(CollapseArgs A, uint32_t lb, uint32_t le) {
   if (w < le) collapse_body(w, A);
 }
 __global__ void k_set_u32(uint32_t* p, uint32_t v) { *p = v; }
+// Input validation for set_scene: flags a mesh whose index buffer points past its vertex array, so
+// that a malformed scene is an error instead of an out-of-bounds read in k_make_tris.
+__global__ void k_check_indices(const uint32_t* __restrict__ tris, uint64_t n_indices, uint32_t nV, uint32_t* __restrict__ flag) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_indices && tris[i] >= nV) *flag = 1u;
+}
 __global__ void k_gather_tris(const F4* __restrict__ soup, const uint32_t* __restrict__ leaf_prims, uint32_t n,
                               uint32_t soup_offset, F4* __restrict__ out) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -513,8 +514,30 @@ int aobake_set_scene(AoBake* ctx, const AoScene* scene, const AoScene* blockers)
   add_insts(scene, ctx->insts);
   if (blockers) add_insts(blockers, binsts);
   for (const HostInstance& I : ctx->insts) ctx->inst_num_verts.push_back(ctx->meshes[I.mesh].nV);
+  for (const std::vector<HostInstance>* v : {&ctx->insts, &binsts})
+    for (const HostInstance& I : *v)
+      for (int k = 0; k < 12; k++)
+        if (!std::isfinite(I.xf[k]) || !std::isfinite(I.inv[k]))
+          return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "instance %zu of the %s has a singular or non-finite transform", (size_t)(&I - v->data()),
+                           v == &ctx->insts ? "scene" : "blockers");
+  // every triangle index must address a vertex of its mesh
+  const size_t n_all_meshes = ctx->meshes.size() + bmeshes.size();
+  DBuf<uint32_t> d_bad;
+  std::vector<uint32_t> h_bad(std::max<size_t>(n_all_meshes, 1), 0u);
+  CK(d_bad.alloc(h_bad.size()));
+  CK(cudaMemsetAsync(d_bad.p, 0, h_bad.size() * sizeof(uint32_t), st));
+  for (size_t m = 0; m < n_all_meshes; m++) {
+    const DeviceMesh& dm = m < ctx->meshes.size() ? ctx->meshes[m] : bmeshes[m - ctx->meshes.size()];
+    if (dm.nT) k_check_indices<<<grid_for(3 * dm.nT, 256), 256, 0, st>>>(dm.tris.p, 3 * dm.nT, (uint32_t)dm.nV, d_bad.p + m);
+  }
+  CKL();
+  CK(cudaMemcpyAsync(h_bad.data(), d_bad.p, h_bad.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   CK(cudaEventRecord(ctx->ev1, st));
   CK(cudaStreamSynchronize(st));
+  for (size_t m = 0; m < n_all_meshes; m++)
+    if (h_bad[m])
+      return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "%s mesh %zu: a triangle index is >= num_vertices", m < ctx->meshes.size() ? "scene" : "blocker",
+                       m < ctx->meshes.size() ? m : m - ctx->meshes.size());
   CK(cudaEventElapsedTime(&ctx->timings.upload_ms, ctx->ev0, ctx->ev1));
 
   // ---- instancing mode (decision #12) ----
@@ -899,7 +922,10 @@ static int compute_ao_impl(AoBake* ctx, size_t begin, size_t end, int rays_per_s
   }
   ctx->timings.rays_traced = owned_samples * (uint64_t)q * q;
   ctx->timings.trace_ms = 0.f;
-  if (n == 0) return AOBAKE_OK;
+  if (n == 0) {
+    if (ctx->num_samples == 0) ctx->have_ao = true;  // nothing to trace: the (empty) AO array is complete
+    return AOBAKE_OK;
+  }
   if (num_parts > 1) {
     // everything this part does not own reads as zero, so that an all-reduce (sum) assembles ao[]
     CK(cudaMemsetAsync(ctx->d_hits.p + begin, 0, n * sizeof(uint32_t), st));

@@ -246,6 +246,37 @@ def test_edge_cases(api):
         assert np.isfinite(ao).all()
 
 
+def test_malformed_scenes_are_errors_not_faults(api):
+    v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], dtype=np.float32)
+    good = Mesh(v, np.array([[0, 1, 2]], dtype=np.uint32))
+    bad_index = Mesh(v, np.array([[0, 1, 3]], dtype=np.uint32))           # index 3 of 3 vertices
+    singular = np.eye(4, dtype=np.float32)
+    singular[2, 2] = 0.0
+    nan_xf = np.eye(4, dtype=np.float32)
+    nan_xf[0, 3] = np.nan
+    with api.Baker() as bk:
+        for scene, blockers in [(Scene([bad_index], [Instance(0)]), None),
+                                (Scene([good], [Instance(0)]), Scene([bad_index], [Instance(0)])),
+                                (Scene([good], [Instance(0, singular)]), None),
+                                (Scene([good], [Instance(0, nan_xf)]), None)]:
+            with pytest.raises(api.AoBakeError) as e:
+                bk.set_scene(scene, blockers)
+            assert e.value.code == 1   # AOBAKE_ERR_INVALID_ARGUMENT
+            with pytest.raises(api.AoBakeError):
+                bk.compute_ao(16, 1e-3, 1.0)      # the failed set_scene left no scene behind
+        # the context is still usable afterwards (no sticky CUDA error)
+        bk.set_scene(Scene([good], [Instance(0)]))
+        total, per = bk.distribute_samples(4, 0)
+        bk.sample_instances(per, 4)
+        assert np.all(bk.compute_ao(16, 1e-3, 10.0) == 1.0)
+        # an empty sample set maps to all-zero vertex AO instead of a state error
+        total, per = bk.distribute_samples(0, 0)
+        bk.sample_instances(per, 0)
+        assert bk.compute_ao(16, 1e-3, 10.0).size == 0
+        assert np.all(bk.map_ao_to_vertices(api.FILTER_AREA_BASED)[0] == 0.0)
+        assert np.all(bk.map_ao_to_vertices(api.FILTER_LEAST_SQUARES, 0.1)[0] == 0.0)
+
+
 def test_strided_vertices(api):
     scene, blockers = SCENES["sphere_ground"]
     m = scene.meshes[0]
