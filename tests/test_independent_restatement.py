@@ -1,0 +1,357 @@
+"""Second, independent restatement of the path in pure Python / numpy, written from the algorithm
+text of SURVEY.md §8(a) and BASELINE.md rather than from oracle/ao_oracle.cpp, and checked against
+the C++ oracle.  The reference mount holds no sources and no golden vectors ("parity unpinned",
+DESIGN.md §2), so this is the strongest pin available here: two implementations in two languages
+that must agree — bit for bit where the arithmetic is specified (RNG, Halton, barycentrics, sample
+positions), within fp64 round-off where the oracle's formula is one of several equivalent ones
+(Möller–Trumbore against Woop, a dense direct solve against Jacobi-PCG).
+
+Small cases only (pure-Python loops)."""
+import numpy as np
+import pytest
+
+from optix_prime_baking_b200 import scenes
+from optix_prime_baking_b200.scenes import Instance, Mesh, Scene
+from tests.oracle_binding import Oracle
+
+f32 = np.float32
+M32 = 0xFFFFFFFF
+
+
+# ---- a8: random.h --------------------------------------------------------------------------
+def py_tea(rounds, v0, v1):
+    s0 = 0
+    for _ in range(rounds):
+        s0 = (s0 + 0x9E3779B9) & M32
+        v0 = (v0 + ((((v1 << 4) + 0xA341316C) & M32) ^ ((v1 + s0) & M32) ^ (((v1 >> 5) + 0xC8013EA4) & M32))) & M32
+        v1 = (v1 + ((((v0 << 4) + 0xAD90777D) & M32) ^ ((v0 + s0) & M32) ^ (((v0 >> 5) + 0x7E95761E) & M32))) & M32
+    return v0
+
+
+class Lcg:
+    def __init__(self, seed):
+        self.s = seed & M32
+
+    def rnd(self):
+        self.s = (1664525 * self.s + 1013904223) & M32
+        return f32(self.s & 0x00FFFFFF) / f32(16777216.0)
+
+
+def py_halton(i, base):
+    inv = f32(1.0) / f32(base)
+    f, r = inv, f32(0.0)
+    while i:
+        r = r + f * f32(i % base)
+        i //= base
+        f = f * inv
+    return r
+
+
+def _frac(x):
+    return x - np.floor(x)
+
+
+def _dot(a, b):
+    return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]
+
+
+def _cross(a, b):
+    return np.array([a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]], dtype=f32)
+
+
+def _normalize(a):
+    n = np.sqrt(_dot(a, a))
+    return a / n if n > 0 else a
+
+
+def _xf_point(m, v):
+    return np.array([((m[r, 0] * v[0] + m[r, 1] * v[1]) + m[r, 2] * v[2]) + m[r, 3] for r in range(3)], dtype=f32)
+
+
+def _inverse_transpose_apply(inv, n):
+    return np.array([(inv[0, c] * n[0] + inv[1, c] * n[1]) + inv[2, c] * n[2] for c in range(3)], dtype=f32)
+
+
+# ---- a5–a7: budget and placement -------------------------------------------------------------
+def py_sample_instance(mesh: Mesh, xform, inst_index, n_samples, min_per_tri):
+    """distribute_samples_generic over the triangles of one instance + sample_triangle."""
+    xf = xform.astype(f32)
+    inv = np.linalg.inv(xf.astype(np.float64))[:3, :3].astype(f32)     # fp64 inverse, rounded once
+    V = mesh.vertices
+    w = np.array([[_xf_point(xf, V[i]) for i in tri] for tri in mesh.tris], dtype=f32)
+    areas = []
+    for t in range(len(mesh.tris)):
+        c = _cross(w[t, 1] - w[t, 0], w[t, 2] - w[t, 0]).astype(np.float64)
+        areas.append(0.5 * np.sqrt((c[0] * c[0] + c[1] * c[1]) + c[2] * c[2]))
+    total = 0.0
+    for b in range(0, len(areas), 1024):          # decision #3: fixed-shape fp64 sum
+        s = 0.0
+        for a in areas[b:b + 1024]:
+            s = s + a
+        total = total + s
+    nT = len(areas)
+    N = max(n_samples, min_per_tri * nT)
+    Na = N - min_per_tri * nT
+    counts = [min_per_tri + (int((float(Na) * a) / total) if Na > 0 and total > 0 else 0) for a in areas]
+    left = N - sum(counts)
+    i = 0
+    while left > 0:
+        counts[i] += 1
+        i = (i + 1) % nT
+        left -= 1
+    out = []
+    for t, c in enumerate(counts):
+        if not c:
+            continue
+        p = [V[k] for k in mesh.tris[t]]
+        fn = _normalize(_cross(p[1] - p[0], p[2] - p[0]))
+        if mesh.normals is not None:
+            n = [mesh.normals[k] for k in mesh.tris[t]]
+            n = [(-x if _dot(x, fn) < 0 else x) for x in n]       # faceforward
+        else:
+            n = [fn, fn, fn]
+        fnw = _normalize(_inverse_transpose_apply(inv, fn))
+        g = Lcg(py_tea(4, inst_index, t))
+        ox, oy = g.rnd(), g.rnd()
+        dA = f32(areas[t] / float(c))
+        for k in range(c):
+            r1 = _frac(ox + py_halton(k + 1, 2))
+            r2 = _frac(oy + py_halton(k + 1, 3))
+            s = np.sqrt(r1)
+            b0 = f32(1.0) - s
+            b1 = r2 * s
+            b2 = (f32(1.0) - b0) - b1
+            po = np.array([(b0 * p[0][a] + b1 * p[1][a]) + b2 * p[2][a] for a in range(3)], dtype=f32)
+            no = np.array([(b0 * n[0][a] + b1 * n[1][a]) + b2 * n[2][a] for a in range(3)], dtype=f32)
+            out.append((t, (b0, b1, b2), dA, _xf_point(xf, po), _normalize(_inverse_transpose_apply(inv, no)), fnw))
+    return counts, out
+
+
+def _small_instanced_scene():
+    m = scenes.uv_sphere(6, 8, radius=0.7)                       # has vertex normals
+    h = scenes.heightfield(5, seed=4, height=0.3)                # none
+    a = np.eye(4, dtype=f32)
+    a[:3, :3] = np.array([[0.0, -1.5, 0.0], [1.2, 0.0, 0.0], [0.0, 0.0, 0.8]], dtype=f32)   # rotate + non-uniform scale
+    a[:3, 3] = [0.3, -2.0, 1.1]
+    b = np.eye(4, dtype=f32)
+    b[:3, :3] = np.array([[1.0, 0.2, 0.0], [0.0, 1.0, 0.3], [0.1, 0.0, 1.0]], dtype=f32)   # shear
+    b[:3, 3] = [4.0, 0.5, -0.25]
+    return Scene([m, h], [Instance(0, a), Instance(1, b), Instance(0)])
+
+
+def test_sample_placement_bit_exact_against_python_restatement():
+    scene = _small_instanced_scene()
+    orc = Oracle(scene)
+    for min_per_tri, requested in [(2, 0), (0, 777), (1, 1500)]:
+        total, per = orc.distribute_samples(min_per_tri, requested)
+        sb = orc.sample_instances(per, min_per_tri)
+        base = 0
+        for i, inst in enumerate(scene.instances):
+            mesh = scene.meshes[inst.mesh_index]
+            counts, smp = py_sample_instance(mesh, inst.xform, i, int(per[i]), min_per_tri)
+            assert len(smp) == int(per[i])
+            assert np.array_equal(orc.triangle_counts(i, int(per[i]), min_per_tri), np.array(counts, dtype=np.uint64))
+            sl = slice(base, base + len(smp))
+            assert np.array_equal(sb.infos["tri_idx"][sl], np.array([s[0] for s in smp], dtype=np.uint32))
+            assert np.array_equal(sb.infos["bary"][sl].view(np.uint32), np.array([s[1] for s in smp], dtype=f32).view(np.uint32))
+            assert np.array_equal(sb.infos["dA"][sl].view(np.uint32), np.array([s[2] for s in smp], dtype=f32).view(np.uint32))
+            assert np.array_equal(sb.positions[sl].view(np.uint32), np.array([s[3] for s in smp], dtype=f32).view(np.uint32))
+            # normals go through the 3x3 inverse: numpy's LU inverse and the oracle's cofactor
+            # inverse agree to fp64 round-off, i.e. to an ulp or two after rounding to fp32
+            assert np.abs(sb.normals[sl] - np.array([s[4] for s in smp])).max() < 5e-7
+            assert np.abs(sb.face_normals[sl] - np.array([s[5] for s in smp])).max() < 5e-7
+            base += len(smp)
+        assert base == total
+
+
+# ---- a9: ray generation ------------------------------------------------------------------------
+def py_ray(pos, nrm, fnrm, sample_index, px, py, q, offset, maxdist):
+    pass_ = px * q + py
+    g = Lcg(py_tea(2, ((pass_ << 16) | pass_) & M32, sample_index))
+    n = nrm.astype(f32)
+    b = np.array([-n[1], n[0], 0], dtype=f32) if abs(n[0]) > abs(n[2]) else np.array([0, -n[2], n[1]], dtype=f32)
+    b = _normalize(b)
+    t = _cross(b, n)
+    u0 = (f32(px) + g.rnd()) / f32(q)
+    u1 = (f32(py) + g.rnd()) / f32(q)
+    d = None
+    for _ in range(5):                                            # decision #5
+        r = np.sqrt(u0)
+        phi = 2.0 * np.pi * float(u1)
+        x, y = f32(float(r) * np.cos(phi)), f32(float(r) * np.sin(phi))
+        z = np.sqrt(max(f32(0.0), (f32(1.0) - x * x) - y * y))
+        d = np.array([(x * t[a] + y * b[a]) + z * n[a] for a in range(3)], dtype=f32)
+        if _dot(d, fnrm.astype(f32)) > 0:
+            break
+        u0, u1 = g.rnd(), g.rnd()
+    o = pos.astype(f32) + f32(offset) * n
+    return np.concatenate([o, [f32(0.0)], d, [f32(maxdist)]]).astype(f32)
+
+
+def test_ray_generation_against_python_restatement():
+    scene = _small_instanced_scene()
+    orc = Oracle(scene)
+    _, per = orc.distribute_samples(1, 0)
+    sb = orc.sample_instances(per, 1)
+    q = 5
+    pick = np.linspace(0, sb.n - 1, 40).astype(int)
+    worst = 0.0
+    for k in pick:
+        rays = orc.generate_rays(sb, int(k), int(k) + 1, q * q, 0.013, 7.5)[0]
+        for px in range(q):
+            for py in range(q):
+                want = py_ray(sb.positions[k], sb.normals[k], sb.face_normals[k], int(k), px, py, q, 0.013, 7.5)
+                got = rays[px * q + py]
+                assert np.array_equal(got[[0, 1, 2, 3, 7]].view(np.uint32), want[[0, 1, 2, 3, 7]].view(np.uint32))
+                worst = max(worst, float(np.abs(got[4:7] - want[4:7]).max()))
+    # directions: the oracle pins a polynomial sincos (decision #11), this file uses libm in fp64;
+    # z = sqrt(1 - x^2 - y^2) amplifies the ~1e-7 difference in (x, y) by 1/z near the horizon
+    assert worst < 1e-5
+
+
+# ---- a10: any-hit, Möller–Trumbore in fp64 against the oracle's watertight Woop test -------------
+def _moller_trumbore_any(tris, o, d, tmax):
+    """tris (T,3,3) fp64; returns (hit, margin) with margin = distance from the decision boundary in
+    barycentric / parametric units (small = too close to an edge or to t = 0 / tmax to call)."""
+    e1, e2 = tris[:, 1] - tris[:, 0], tris[:, 2] - tris[:, 0]
+    pv = np.cross(d, e2)
+    det = (e1 * pv).sum(axis=1)
+    ok = np.abs(det) > 1e-14
+    inv = np.where(ok, 1.0 / np.where(ok, det, 1.0), 0.0)
+    tv = o - tris[:, 0]
+    u = (tv * pv).sum(axis=1) * inv
+    qv = np.cross(tv, e1)
+    v = (qv * d).sum(axis=1) * inv
+    t = (qv * e2).sum(axis=1) * inv
+    inside = np.minimum.reduce([u, v, 1.0 - u - v, t / tmax, 1.0 - t / tmax])
+    inside = np.where(ok, inside, -1.0)
+    return bool((inside > 0).any()), float(np.abs(inside).min())
+
+
+def test_any_hit_against_fp64_moller_trumbore():
+    scene, blk = scenes.config4_instanced(grid=2, stacks=8, slices=8, with_ground=True)
+    tris = []
+    for sc in (scene, blk):
+        for inst in sc.instances:
+            m = sc.meshes[inst.mesh_index]
+            w = m.vertices.astype(np.float64) @ inst.xform[:3, :3].T.astype(np.float64) + inst.xform[:3, 3].astype(np.float64)
+            tris.append(w[m.tris])
+    tris = np.concatenate(tris)
+    rng = np.random.default_rng(11)
+    lo, hi = scene.world_bbox()
+    ext = float((hi - lo).max())
+    n = 3000
+    rays = np.zeros((n, 8), dtype=f32)
+    rays[:, 0:3] = rng.uniform(lo - 0.3 * ext, hi + 0.3 * ext, (n, 3))
+    d = rng.normal(size=(n, 3))
+    rays[:, 4:7] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    rays[:, 7] = rng.uniform(0.1 * ext, 2.5 * ext, n)
+    checked = 0
+    for mode in (1, 2):                                           # flattened, then TLAS/BLAS
+        orc = Oracle(scene, blk, mode)
+        got_bvh, got_brute = orc.trace_rays(rays), orc.trace_rays(rays, brute=True)
+        for k in range(n):
+            hit, margin = _moller_trumbore_any(tris, rays[k, 0:3].astype(np.float64), rays[k, 4:7].astype(np.float64), float(rays[k, 7]))
+            if margin < 1e-4:                                     # too close to an edge to be a fair test of fp32
+                continue
+            assert bool(got_bvh[k]) == hit and bool(got_brute[k]) == hit, (mode, k, margin)
+            checked += 1
+    assert checked > 0.95 * 2 * n
+    assert 0.1 < got_bvh.mean() < 0.9                             # the ray set exercises both outcomes
+
+
+# ---- a15/a16: vertex maps, dense fp64 -----------------------------------------------------------
+def _dense_least_squares(mesh: Mesh, xform, infos, ao, weight):
+    nV = len(mesh.vertices)
+    M = np.zeros((nV, nV))
+    b = np.zeros(nV)
+    for si, a in zip(infos, ao):
+        idx = mesh.tris[si["tri_idx"]]
+        bary = si["bary"].astype(np.float64)
+        M[np.ix_(idx, idx)] += float(si["dA"]) * np.outer(bary, bary)
+        b[idx] += float(si["dA"]) * float(a) * bary
+    for v in range(nV):                                           # decision #7
+        if not M[v, v] > 0:
+            M[v, v] = 1.0
+            b[v] = 0.0
+    W = mesh.vertices.astype(f32)
+    xf = xform.astype(f32)
+    W = np.array([_xf_point(xf, v) for v in W], dtype=np.float64)
+    # interior edges: the two triangles (lowest indices) sharing an undirected edge
+    edge_tris = {}
+    for t, tri in enumerate(mesh.tris):
+        for e in range(3):
+            a_, b_ = int(tri[e]), int(tri[(e + 1) % 3])
+            if a_ != b_:
+                edge_tris.setdefault((min(a_, b_), max(a_, b_)), []).append((t, int(tri[(e + 2) % 3])))
+    R = np.zeros((nV, nV))
+    for (i, j), lst in edge_tris.items():
+        if len(lst) < 2:
+            continue
+        (_, p), (_, q) = sorted(lst)[:2]
+        e = W[j] - W[i]
+        row = np.zeros(nV)
+        area = 0.0
+        ok = np.dot(e, e) > 0
+        for o in (p, q):
+            # gradient of the linear interpolant over triangle (i, j, o), as a map from vertex
+            # values to a 3-vector: solve the 2 edge equations in the triangle's plane
+            E = np.stack([W[j] - W[i], W[o] - W[i]])               # 2x3
+            G = np.linalg.pinv(E)                                   # 3x2: grad = G @ [x_j - x_i, x_o - x_i]
+            foot = W[i] + e * (np.dot(W[o] - W[i], e) / np.dot(e, e))
+            h = np.linalg.norm(W[o] - foot)
+            if not h > 0:
+                ok = False
+                break
+            m = (W[o] - foot) / h                                   # in-plane co-normal, pointing into the triangle
+            gm = m @ G                                              # d/dm = gm[0]*(x_j - x_i) + gm[1]*(x_o - x_i)
+            row[j] += gm[0]
+            row[o] += gm[1]
+            row[i] -= gm[0] + gm[1]
+            area += 0.5 * np.linalg.norm(e) * h
+        if ok:
+            R += area * area * np.outer(row, row)                   # decision #6: (A1+A2)^2 J^T J
+    return np.linalg.solve(M + weight * R, b), R
+
+
+@pytest.mark.parametrize("weight", [0.0, 0.1, 3.0])
+def test_least_squares_filter_against_dense_direct_solve(weight):
+    m = scenes.heightfield(7, seed=9, height=0.4)
+    xf = np.eye(4, dtype=f32)
+    xf[:3, :3] = np.array([[1.3, 0.0, 0.2], [0.0, 0.9, 0.0], [-0.1, 0.0, 1.1]], dtype=f32)
+    scene = Scene([m], [Instance(0, xf)])
+    orc = Oracle(scene)
+    _, per = orc.distribute_samples(0, 60)                        # < 1 sample per triangle: some vertices unsampled
+    sb = orc.sample_instances(per, 0)
+    rng = np.random.default_rng(5)
+    ao = rng.uniform(0.1, 1.0, sb.n).astype(f32)
+    want, R = _dense_least_squares(m, xf, sb.infos, ao, weight)
+    got = orc.filter_least_squares(sb, ao, weight=weight, tol=1e-13)[0]
+    assert np.abs(got - want).max() < 2e-6
+    # the regulariser annihilates fields that are linear in world space on a planar mesh
+    if weight:
+        flat = scenes.heightfield(7, seed=9, height=0.0)
+        _, Rf = _dense_least_squares(flat, xf, sb.infos[:0], ao[:0], weight)
+        Wf = flat.vertices.astype(np.float64) @ xf[:3, :3].T.astype(np.float64)
+        lin = 0.3 + Wf @ np.array([0.2, -0.7, 0.05])
+        assert np.abs(Rf @ lin).max() < 1e-6 * np.abs(Rf).max()    # world positions are rounded to fp32
+
+
+def test_area_filter_against_numpy():
+    scene = _small_instanced_scene()
+    orc = Oracle(scene)
+    _, per = orc.distribute_samples(2, 0)
+    sb = orc.sample_instances(per, 2)
+    ao = np.random.default_rng(2).uniform(0, 1, sb.n).astype(f32)
+    got = orc.filter_area(sb, ao)
+    base = 0
+    for i, inst in enumerate(scene.instances):
+        m = scene.meshes[inst.mesh_index]
+        sl = slice(base, base + int(per[i]))
+        idx = m.tris[sb.infos["tri_idx"][sl]]
+        w = sb.infos["bary"][sl].astype(np.float64) * sb.infos["dA"][sl].astype(np.float64)[:, None]
+        num = np.bincount(idx.ravel(), weights=(w * ao[sl].astype(np.float64)[:, None]).ravel(), minlength=len(m.vertices))
+        den = np.bincount(idx.ravel(), weights=w.ravel(), minlength=len(m.vertices))
+        want = np.where(den > 0, num / np.where(den > 0, den, 1), 0)
+        assert np.abs(got[i] - want).max() < 1e-6
+        base += int(per[i])
