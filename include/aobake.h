@@ -117,7 +117,9 @@ typedef struct AoBakeParams {
   int32_t collect_stats;          /* 1: count node visits / triangle tests in aobake_compute_ao */
   int32_t refill_below;           /* persistent kernel: refill a warp when fewer lanes are traversing (0 = default 28) */
   int32_t leaf_tris;              /* triangles per leaf slot of the 8-wide BVH, 1..3 (0 = default: 2 flattened, 1 per BLAS) */
-  int32_t reserved[6];
+  int32_t node_test;              /* box test of the fused kernel: 0 = auto (packed fp16, two planes per instruction; the few
+                                     rays outside its range are traced by a second small launch in fp32), 1 = fp32 only */
+  int32_t reserved[5];
 } AoBakeParams;
 
 typedef struct AoTimings {        /* milliseconds, device-timed with CUDA events unless noted */

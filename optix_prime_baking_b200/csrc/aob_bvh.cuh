@@ -17,6 +17,9 @@
 #pragma once
 #include "aob_math.cuh"
 #include <string.h>
+#if defined(__CUDACC__)
+#include <cuda_fp16.h>
+#endif
 
 namespace aob {
 
@@ -38,6 +41,17 @@ AOB_D int popc32(uint32_t v) { return __popc(v); }
 AOB_D int ffs32(uint32_t v) { return __ffs((int)v); }
 AOB_D uint32_t atomic_add_u32(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
 AOB_D void thread_fence() { __threadfence(); }
+// PRMT with a register selector (no 0x7777 masking as in __byte_perm: selectors here never set bit 3)
+AOB_D uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) { uint32_t r; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(s)); return r; }
+// packed fp16 pairs for the node test: F2FP.SATFINITE / HFMA2 / HMNMX2 / HADD2 with lane swizzles
+AOB_D uint32_t h2_pack_sat(float hi, float lo) { uint32_t r; asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo)); return r; }
+AOB_D uint32_t h2_fma(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+AOB_D uint32_t h2_min(uint32_t a, uint32_t b) { uint32_t r; asm("min.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+AOB_D uint32_t h2_lane_sum(uint32_t a) {  // lane0 + lane1, in both lanes (HADD2 R, R.H0_H0, R.H1_H1)
+  const __half2 h = *reinterpret_cast<const __half2*>(&a);
+  const __half2 r = __hadd2(__low2half2(h), __high2half2(h));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
 #else
 inline U4 ld_u4(const U4* p) { return *p; }
 inline F4 ld_f4(const F4* p) { return *p; }
@@ -56,6 +70,58 @@ inline int popc32(uint32_t v) { return __builtin_popcount(v); }
 inline int ffs32(uint32_t v) { return __builtin_ffs((int)v); }
 inline uint32_t atomic_add_u32(uint32_t* p, uint32_t v) { uint32_t o = *p; *p += v; return o; }
 inline void thread_fence() {}
+inline uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) { return byte_perm(a, b, s); }
+// fp16 emulation for tests/emu: exact decode, round-to-nearest-even encode from a double (the
+// products of two halves are exact in a double; the one rounding of an fp16 FMA is reproduced up to
+// double rounding in cases that need more than 53 bits, which the padding of the node test covers).
+inline double h_to_d(uint32_t h) {
+  const uint32_t sgn = (h >> 15) & 1u, e = (h >> 10) & 31u, m = h & 1023u;
+  double v;
+  if (e == 0) v = ldexp((double)m, -24);
+  else if (e == 31) v = m ? NAN : INFINITY;
+  else v = ldexp((double)(m | 1024u), (int)e - 25);
+  return sgn ? -v : v;
+}
+inline uint32_t d_to_h(double x, bool satfinite) {
+  if (x != x) return 0x7fffu;
+  const uint32_t sgn = signbit(x) ? 0x8000u : 0u;
+  double a = fabs(x);
+  if (a >= 65520.0) return sgn | (satfinite ? 0x7bffu : 0x7c00u);   // 65520 = halfway to 2^16: rounds to inf
+  if (a < ldexp(1.0, -14)) {   // subnormal half: multiples of 2^-24
+    const double r = nearbyint(ldexp(a, 24));   // ties to even (default rounding mode)
+    return sgn | (uint32_t)r;                   // r == 1024 encodes the smallest normal: still correct
+  }
+  int e;
+  const double f = frexp(a, &e);                // a = f * 2^e, f in [0.5, 1)
+  double m = nearbyint(ldexp(f, 11));           // 11 significant bits: [1024, 2048]
+  if (m == 2048.0) { m = 1024.0; e += 1; }
+  const int be = e - 1 + 15;                    // biased exponent of 1.xxx * 2^(e-1)
+  if (be >= 31) return sgn | (satfinite ? 0x7bffu : 0x7c00u);
+  return sgn | ((uint32_t)be << 10) | ((uint32_t)m - 1024u);
+}
+inline uint32_t h2_pack_sat(float hi, float lo) { return (d_to_h(hi, true) << 16) | d_to_h(lo, true); }
+inline uint32_t h2_fma(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r = 0;
+  for (int l = 0; l < 2; l++) {
+    const int sh = 16 * l;
+    r |= d_to_h(h_to_d((a >> sh) & 0xffffu) * h_to_d((b >> sh) & 0xffffu) + h_to_d((c >> sh) & 0xffffu), false) << sh;
+  }
+  return r;
+}
+inline uint32_t h2_min(uint32_t a, uint32_t b) {
+  uint32_t r = 0;
+  for (int l = 0; l < 2; l++) {
+    const int sh = 16 * l;
+    const uint32_t x = (a >> sh) & 0xffffu, y = (b >> sh) & 0xffffu;
+    const double dx = h_to_d(x), dy = h_to_d(y);
+    r |= ((dx != dx) ? y : (dy != dy) ? x : (dy < dx ? y : x)) << sh;
+  }
+  return r;
+}
+inline uint32_t h2_lane_sum(uint32_t a) {
+  const uint32_t h = d_to_h(h_to_d(a & 0xffffu) + h_to_d(a >> 16), false);
+  return (h << 16) | h;
+}
 #endif
 
 // ---- node layout ---------------------------------------------------------------------
@@ -66,8 +132,10 @@ struct alignas(16) Node8 {
   uint32_t child_base;         // index of the first internal child (children contiguous, slot order)
   uint32_t prim_base;          // index of the first leaf primitive referenced by this node
   uint8_t meta[8];             // 0 empty | internal: 0x20|(24+slot) | leaf: unary(count)<<5 | offset
-  uint8_t qlox[8], qloy[8], qloz[8];
-  uint8_t qhix[8], qhiy[8], qhiz[8];
+  // child boxes on the parent's 8-bit grid, [axis][slot][0 = lo, 1 = hi]: the lo and hi bytes of a
+  // slot sit side by side so that ONE byte permute yields the (near, far) pair of a child as two
+  // fp16 lanes (intersect_node8_h2); words 2j, 2j+1 of an axis hold slots 2j and 2j+1.
+  uint8_t q[3][8][2];
 };
 static_assert(sizeof(Node8) == 80, "Node8 must be 80 bytes");
 
@@ -75,6 +143,7 @@ constexpr uint32_t kLeafBit = 0x80000000u;
 constexpr uint32_t kSentinel = 0xFFFFFFFFu;
 constexpr int kStackSize = 48;
 constexpr int kInstF4 = 5;  // float4s per instance record
+constexpr int kExpSpread = 14;  // max log2 ratio between the grid steps of one node (see collapse_body)
 
 struct BvhView {
   const U4* nodes;   // 5 x U4 per node
@@ -294,7 +363,18 @@ AOB_HD void collapse_body(uint32_t w, const CollapseArgs& A) {
   uint32_t pbase = n_prims ? atomic_add_u32(A.prim_count, n_prims) : 0u;
   Node8 nd;
   nd.px = nlo.x; nd.py = nlo.y; nd.pz = nlo.z;
-  const uint32_t ex = quant_exponent(nhi.x - nlo.x), ey = quant_exponent(nhi.y - nlo.y), ez = quant_exponent(nhi.z - nlo.z);
+  uint32_t ex = quant_exponent(nhi.x - nlo.x), ey = quant_exponent(nhi.y - nlo.y), ez = quant_exponent(nhi.z - nlo.z);
+  {
+    // Keep the three grid steps within 2^kExpSpread of the widest one (and the widest away from
+    // zero).  The fp16 node test works in a frame scaled by the widest axis and needs every
+    // per-axis step to be a normal fp16 number there; a step 2^-14 of the widest one is far below
+    // anything that changes which rays meet the box.
+    uint32_t em = ex > ey ? ex : ey;
+    em = em > ez ? em : ez;
+    if (em < 24u) em = 24u;
+    const uint32_t fl = em - (uint32_t)kExpSpread;
+    ex = ex > fl ? ex : fl; ey = ey > fl ? ey : fl; ez = ez > fl ? ez : fl;
+  }
   nd.ex = (uint8_t)ex; nd.ey = (uint8_t)ey; nd.ez = (uint8_t)ez;
   nd.child_base = A.node_offset + cbase;
   nd.prim_base = A.prim_offset + pbase;
@@ -302,15 +382,14 @@ AOB_HD void collapse_body(uint32_t w, const CollapseArgs& A) {
   for (int k = 0; k < 8; k++) {
     if (k >= ns) {
       nd.meta[k] = 0;
-      nd.qlox[k] = nd.qloy[k] = nd.qloz[k] = 255;
-      nd.qhix[k] = nd.qhiy[k] = nd.qhiz[k] = 0;
+      for (int a = 0; a < 3; a++) { nd.q[a][k][0] = 255; nd.q[a][k][1] = 0; }
       continue;
     }
     F4 lo, hi;
     lbvh_ref_box(L, slot[k], &lo, &hi);
-    quantize_axis(nlo.x, ex, lo.x, hi.x, &nd.qlox[k], &nd.qhix[k]);
-    quantize_axis(nlo.y, ey, lo.y, hi.y, &nd.qloy[k], &nd.qhiy[k]);
-    quantize_axis(nlo.z, ez, lo.z, hi.z, &nd.qloz[k], &nd.qhiz[k]);
+    quantize_axis(nlo.x, ex, lo.x, hi.x, &nd.q[0][k][0], &nd.q[0][k][1]);
+    quantize_axis(nlo.y, ey, lo.y, hi.y, &nd.q[1][k][0], &nd.q[1][k][1]);
+    quantize_axis(nlo.z, ez, lo.z, hi.z, &nd.q[2][k][0], &nd.q[2][k][1]);
     if (area[k] >= 0.0f) {
       imask |= 1u << k;
       nd.meta[k] = (uint8_t)(0x20u | (24u + (uint32_t)k));
@@ -341,6 +420,8 @@ struct RayState {
   V3 org, dir;
   float tmin, tmax;
   V3 idir;     // clamped reciprocal for the slab tests
+  bool wide;   // fp16 node test not applicable (a direction component below 2^-12, or a non-rigid
+               // instance transform): use the fp32 test for this ray
 };
 AOB_HD float safe_rcp(float d) {  // for the slab tests only; their padding absorbs 2 ulp here
   const float tiny = 1e-18f;
@@ -353,9 +434,18 @@ AOB_HD float safe_rcp(float d) {  // for the slab tests only; their padding abso
   return 1.0f / a;
 #endif
 }
+// |idir| above this (a direction component below 2^-12) sends the ray to the fp32 node test: the
+// fp16 test keeps |A| = 8 |idir| inside the fp16 range only up to here.  About 5 rays in 10^4.
+constexpr float kH2MaxIdir = 4096.0f;
+AOB_HD bool ray_is_wide(V3 dir, V3 idir) {
+  const float m = fmaxf(fmaxf(fabsf(idir.x), fabsf(idir.y)), fabsf(idir.z));
+  const float d2 = (dir.x * dir.x + dir.y * dir.y) + dir.z * dir.z;   // object-space rays: rigid instances only
+  return !(m <= kH2MaxIdir) || !(fabsf(d2 - 1.0f) <= 1.0e-3f);
+}
 AOB_HD void ray_setup(RayState& r, V3 org, V3 dir, float tmin, float tmax) {
   r.org = org; r.dir = dir; r.tmin = tmin; r.tmax = tmax;
   r.idir = v3(safe_rcp(dir.x), safe_rcp(dir.y), safe_rcp(dir.z));
+  r.wide = ray_is_wide(dir, r.idir);
 }
 
 // Constants of the node test, pinned in registers once per thread: ptxas otherwise re-materialises
@@ -381,9 +471,6 @@ AOB_D NodeConsts make_node_consts() {
 #endif
   return c;
 }
-AOB_D float q2f(uint32_t word, int k, const NodeConsts& c) {  // 32768 + byte k of word, as float (no int->float convert)
-  return as_float(byte_perm(word, c.k47, 0x7404u | ((uint32_t)k << 4)));
-}
 // (hi << 1) | (lo >> 31): shifts the sign bit of `lo` into an accumulator with one SHF
 AOB_D uint32_t shift_in_sign(uint32_t acc, uint32_t lo) {
 #if defined(__CUDA_ARCH__)
@@ -392,9 +479,22 @@ AOB_D uint32_t shift_in_sign(uint32_t acc, uint32_t lo) {
   return (acc << 1) | (lo >> 31);
 #endif
 }
+// Expands the 8 slot hit bits into the traversal mask [31:24] internal slots | [23:0] leaf primitive bits.
+AOB_D uint32_t expand_hit_bits(uint32_t hb, uint32_t im, uint32_t meta_lo, uint32_t meta_hi) {
+  uint32_t hitmask = (hb & im) << 24;
+  uint32_t lh = hb & ~im;
+  while (lh) {
+    const int s = ffs32(lh) - 1;
+    lh &= lh - 1u;
+    const uint32_t m = (((s & 4) ? meta_hi : meta_lo) >> (8 * (s & 3))) & 0xffu;
+    hitmask |= (m >> 5) << (m & 31u);
+  }
+  return hitmask;
+}
 
-// Slab-tests the 8 quantised child boxes of node `idx`; returns the hit mask in the layout
-// [31:24] internal slots | [23:0] leaf primitive bits.
+// Slab-tests the 8 quantised child boxes of node `idx` in fp32; returns the hit mask in the layout
+// [31:24] internal slots | [23:0] leaf primitive bits.  Used for the few rays the fp16 test below
+// cannot take (RayState::wide) and as its cross-check in the emulation tests.
 //
 // Conservative slabs: t(q) = (32768 + q) * ad + o with o = b - 32768 * ad, b = (p - org) * idir,
 // ad = 2^e * idir; the byte q is dropped into the mantissa of 32768.0f with one PRMT (no
@@ -426,39 +526,99 @@ AOB_D uint32_t intersect_node8(const U4* nodes, uint32_t idx, const RayState& r,
   const float pady = fmaf(0.0234375f, fabsf(ady), 1.0e-6f * fabsf(by));
   const float padz = fmaf(0.0234375f, fabsf(adz), 1.0e-6f * fabsf(bz));
   const float onx = ox - padx, ofx = ox + padx, ony = oy - pady, ofy = oy + pady, onz = oz - padz, ofz = oz + padz;
-  const bool nx = r.dir.x < 0.0f, ny = r.dir.y < 0.0f, nz = r.dir.z < 0.0f;
+  // Slot 2j + s of an axis is (lo, hi) = bytes (2s, 2s + 1) of word j.  For a negative direction
+  // component the near plane is the hi byte: swap the two bytes of every pair once per word (one
+  // PRMT with a per-ray selector), so that the 48 decoding PRMTs below keep immediate selectors.
+  const uint32_t swx = r.dir.x < 0.0f ? 0x2301u : 0x3210u, swy = r.dir.y < 0.0f ? 0x2301u : 0x3210u,
+                 swz = r.dir.z < 0.0f ? 0x2301u : 0x3210u;
+  const uint32_t wx[4] = {prmt(n2.x, 0u, swx), prmt(n2.y, 0u, swx), prmt(n2.z, 0u, swx), prmt(n2.w, 0u, swx)};
+  const uint32_t wy[4] = {prmt(n3.x, 0u, swy), prmt(n3.y, 0u, swy), prmt(n3.z, 0u, swy), prmt(n3.w, 0u, swy)};
+  const uint32_t wz[4] = {prmt(n4.x, 0u, swz), prmt(n4.y, 0u, swz), prmt(n4.z, 0u, swz), prmt(n4.w, 0u, swz)};
   // Children are tested from slot 7 down to slot 0; each pushes the sign bit of (tf - tn) into
   // `miss` (one FADD on the FMA pipe + one SHF), so slot s ends up in bit s and a set bit means
   // "missed" (tf < tn).  tf - tn is never NaN (all operands finite) and x - x = +0.
+  // 0x74n4 = (k47.b0, byte n of the word, k47.b2, k47.b3) = 32768 + q as a float.
   uint32_t miss = 0;
 #pragma unroll
-  for (int h = 1; h >= 0; h--) {
-    const uint32_t lox = h ? n2.y : n2.x, loy = h ? n2.w : n2.z, loz = h ? n3.y : n3.x;
-    const uint32_t hix = h ? n3.w : n3.z, hiy = h ? n4.y : n4.x, hiz = h ? n4.w : n4.z;
-    const uint32_t nwx = nx ? hix : lox, fwx = nx ? lox : hix;
-    const uint32_t nwy = ny ? hiy : loy, fwy = ny ? loy : hiy;
-    const uint32_t nwz = nz ? hiz : loz, fwz = nz ? loz : hiz;
+  for (int k = 7; k >= 0; k--) {
+    const uint32_t sn = (k & 1) ? 0x7424u : 0x7404u, sf = (k & 1) ? 0x7434u : 0x7414u;
+    const float tnx = fmaf(as_float(byte_perm(wx[k >> 1], nc.k47, sn)), adx, onx), tfx = fmaf(as_float(byte_perm(wx[k >> 1], nc.k47, sf)), adx, ofx);
+    const float tny = fmaf(as_float(byte_perm(wy[k >> 1], nc.k47, sn)), ady, ony), tfy = fmaf(as_float(byte_perm(wy[k >> 1], nc.k47, sf)), ady, ofy);
+    const float tnz = fmaf(as_float(byte_perm(wz[k >> 1], nc.k47, sn)), adz, onz), tfz = fmaf(as_float(byte_perm(wz[k >> 1], nc.k47, sf)), adz, ofz);
+    const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, r.tmin));
+    const float tf = CLAMP_TMAX ? fminf(fminf(tfx, tfy), fminf(tfz, r.tmax)) : fminf(fminf(tfx, tfy), tfz);
+    miss = shift_in_sign(miss, as_uint(tf - tn));
+  }
+  return expand_hit_bits(~miss & 0xffu, im, n1.z, n1.w);
+}
+
+// The same test in packed fp16, two planes per instruction (HFMA2 / HMNMX2): the (near, far) bytes of
+// a slot are adjacent in the node, so one PRMT against RZ yields them as two fp16 *subnormals*
+// (q * 2^-24, exact, no int->float conversion and no bias to remove); one HFMA2 per axis gives
+// (-tn_a, tf_a), two 3-input minima reduce over the axes and the ray interval, and one HADD2 with
+// lane swizzles gives tf - tn, whose sign bit is the miss bit.  Per slot: 3 PRMT + 3 HFMA2 +
+// 2 HMNMX + 1 HADD2 + 1 SHF, against 6 PRMT + 6 FFMA + 3 FMNMX + 1 FADD + 1 SHF in fp32.
+//
+// fp16 has 11 significant bits, so the planes are evaluated in a frame local to the node:
+//   T = (t - t_c) / W,   t_c = (c - org) . dir  (the ray's closest approach to the grid centre c),
+//   W = 2^21 * (widest grid step) = 2^13 grid widths.
+// If the ray meets the node's box at all, it does so within 0.87 grid widths of t_c, i.e. at
+// |T| <= 1.1e-4, where fp16 resolves 6e-8..1.2e-7 = 1/8..1/4 of the widest axis' quantisation step;
+// far from t_c the resolution degrades but nothing there can turn a hit into a miss.  Plane q of
+// axis a is T = q_h * A + B with q_h = q * 2^-24, A = 2^24 * step_a * idir_a / W (= 8 idir_a on the
+// widest axis, so |idir| <= 4096 keeps A finite; other rays take the fp32 test), B = ((p_a - org_a)
+// * idir_a - t_c) / W.  Conservative by construction: every plane is pushed outwards by
+//   P = 1.6e-8 |A| + 1.0e-3 |B| + 5e-7 |t_c / W| + 6.5e-8
+// which bounds the rounding of A to fp16 (255 * 2^-11 steps), of B and of the FMA result (2^-11
+// relative, or 2^-25 absolute below the fp16 normal range), the fp32 set-up arithmetic including the
+// approximate reciprocal, and the cancellation in B; saturating conversions only ever move a plane
+// that is > 65504 away from a hit (any hit has |B| < 1).  NaN can only arise as inf - inf in the
+// last add, i.e. for a box that is a miss anyway, and reads as a hit.  tests/emu checks this test
+// against brute force and against the fp32 test.
+#ifndef AOB_PADK
+#define AOB_PADK 1.0f
+#endif
+AOB_D uint32_t intersect_node8_h2(const U4* nodes, uint32_t idx, const RayState& r, uint32_t* child_base, uint32_t* prim_base,
+                                  uint32_t* imask) {
+  const U4* p = nodes + 5ull * idx;
+  const U4 n0 = ld_u4(p), n1 = ld_u4(p + 1), n2 = ld_u4(p + 2), n3 = ld_u4(p + 3), n4 = ld_u4(p + 4);
+  *child_base = n1.x;
+  *prim_base = n1.y;
+  const uint32_t im = n0.w >> 24;
+  *imask = im;
+  const float sx = as_float((n0.w & 0xffu) << 23), sy = as_float(((n0.w >> 8) & 0xffu) << 23), sz = as_float(((n0.w >> 16) & 0xffu) << 23);
+  const float smax = fmaxf(fmaxf(sx, sy), sz);
+  const float inv = as_float(0x7f000000u - (21u << 23) - as_uint(smax));   // 1 / W, exact (smax is a power of two >= 2^-103)
+  const float dx = as_float(n0.x) - r.org.x, dy = as_float(n0.y) - r.org.y, dz = as_float(n0.z) - r.org.z;
+  const float tc = fmaf(fmaf(128.0f, sz, dz), r.dir.z, fmaf(fmaf(128.0f, sy, dy), r.dir.y, fmaf(128.0f, sx, dx) * r.dir.x));
+  const float tcs = tc * inv;
+  const float ux = r.idir.x * inv, uy = r.idir.y * inv, uz = r.idir.z * inv;
+  const float ax = (sx * 16777216.0f) * ux, ay = (sy * 16777216.0f) * uy, az = (sz * 16777216.0f) * uz;
+  const float bx = fmaf(dx, ux, -tcs), by = fmaf(dy, uy, -tcs), bz = fmaf(dz, uz, -tcs);
+  const float g = AOB_PADK * fmaf(5.0e-7f, fabsf(tcs), 6.5e-8f);
+  const float px = fmaf(AOB_PADK * 1.6e-8f, fabsf(ax), fmaf(AOB_PADK * 1.0e-3f, fabsf(bx), g));
+  const float py = fmaf(AOB_PADK * 1.6e-8f, fabsf(ay), fmaf(AOB_PADK * 1.0e-3f, fabsf(by), g));
+  const float pz = fmaf(AOB_PADK * 1.6e-8f, fabsf(az), fmaf(AOB_PADK * 1.0e-3f, fabsf(bz), g));
+  // lanes: low = -(near plane), high = far plane
+  const uint32_t A2x = h2_pack_sat(ax, -ax), A2y = h2_pack_sat(ay, -ay), A2z = h2_pack_sat(az, -az);
+  const uint32_t B2x = h2_pack_sat(bx + px, px - bx), B2y = h2_pack_sat(by + py, py - by), B2z = h2_pack_sat(bz + pz, pz - bz);
+  const float q0 = (r.tmin - tc) * inv, q1 = (r.tmax - tc) * inv;
+  const uint32_t Q2 = h2_pack_sat(fmaf(5.2e-4f, fabsf(q1), q1 + 6.5e-8f), fmaf(5.2e-4f, fabsf(q0), 6.5e-8f - q0));
+  // byte selectors: (near byte, 0, far byte, 0) with RZ as the second PRMT source; slot 2j + 1 is +0x0202
+  const uint32_t s0x = r.dir.x < 0.0f ? 0x4041u : 0x4140u, s0y = r.dir.y < 0.0f ? 0x4041u : 0x4140u,
+                 s0z = r.dir.z < 0.0f ? 0x4041u : 0x4140u;
+  const uint32_t wx[4] = {n2.x, n2.y, n2.z, n2.w}, wy[4] = {n3.x, n3.y, n3.z, n3.w}, wz[4] = {n4.x, n4.y, n4.z, n4.w};
+  uint32_t miss = 0;
 #pragma unroll
-    for (int k = 3; k >= 0; k--) {
-      const float tnx = fmaf(q2f(nwx, k, nc), adx, onx), tfx = fmaf(q2f(fwx, k, nc), adx, ofx);
-      const float tny = fmaf(q2f(nwy, k, nc), ady, ony), tfy = fmaf(q2f(fwy, k, nc), ady, ofy);
-      const float tnz = fmaf(q2f(nwz, k, nc), adz, onz), tfz = fmaf(q2f(fwz, k, nc), adz, ofz);
-      const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, r.tmin));
-      const float tf = CLAMP_TMAX ? fminf(fminf(tfx, tfy), fminf(tfz, r.tmax)) : fminf(fminf(tfx, tfy), tfz);
-      miss = shift_in_sign(miss, as_uint(tf - tn));
-    }
+  for (int k = 7; k >= 0; k--) {
+    const uint32_t up = (k & 1) ? 0x0202u : 0u;
+    const uint32_t tx = h2_fma(prmt(wx[k >> 1], 0u, s0x + up), A2x, B2x);
+    const uint32_t ty = h2_fma(prmt(wy[k >> 1], 0u, s0y + up), A2y, B2y);
+    const uint32_t tz = h2_fma(prmt(wz[k >> 1], 0u, s0z + up), A2z, B2z);
+    const uint32_t m = h2_min(h2_min(tx, ty), h2_min(tz, Q2));   // (-tn, tf)
+    miss = shift_in_sign(miss, h2_lane_sum(m));                  // sign(tf - tn)
   }
-  const uint32_t hb = ~miss & 0xffu;
-  // expand the 8 slot bits: internal slots map to bits 24+slot; leaf slots to their primitive bits
-  uint32_t hitmask = (hb & im) << 24;
-  uint32_t lh = hb & ~im;
-  while (lh) {
-    const int s = ffs32(lh) - 1;
-    lh &= lh - 1u;
-    const uint32_t m = (((s & 4) ? n1.w : n1.z) >> (8 * (s & 3))) & 0xffu;
-    hitmask |= (m >> 5) << (m & 31u);
-  }
-  return hitmask;
+  return expand_hit_bits(~miss & 0xffu, im, n1.z, n1.w);
 }
 
 struct TraceCounters {
@@ -523,8 +683,22 @@ AOB_D bool sphere_may_hit(V3 o, V3 d, F4 s) {
   return b * b * 1.00001f >= dd * c;          // discriminant >= 0, with slack for rounding
 }
 
+// Node test selection: AOB_H2 = 1 (default) uses the packed-fp16 test for every ray it applies to
+// and the fp32 test for the rest; 0 builds the fp32 test only.  trace_any_hit (one ray per thread:
+// k_ao_simple, k_trace_rays, the emulation) carries both tests inline and picks per ray; the fused
+// persistent kernel cannot afford the registers of both (96 instead of 72) and instead hands the few
+// rays the fp16 test cannot take to a second, tiny launch (k_ao_deferred).
+#ifndef AOB_H2
+#define AOB_H2 1
+#endif
+template <bool CLAMP_TMAX, bool H2>
+AOB_D uint32_t node_test(const U4* nodes, uint32_t idx, const RayState& r, const NodeConsts& nc, uint32_t* cb, uint32_t* pb, uint32_t* im) {
+  if (H2 && !r.wide) return intersect_node8_h2(nodes, idx, r, cb, pb, im);
+  return intersect_node8<CLAMP_TMAX>(nodes, idx, r, nc, cb, pb, im);
+}
+
 // Any-hit traversal of one ray with a caller-provided stack of kStackSize entries.
-template <bool STATS>
+template <bool STATS, bool H2 = (AOB_H2 != 0)>
 AOB_D bool trace_any_hit(const BvhView& bvh, V3 org, V3 dir, float tmin, float tmax, U2* stack, TraceCounters* cnt) {
   RayState r;
   ray_setup(r, org, dir, tmin, tmax);
@@ -543,7 +717,7 @@ AOB_D bool trace_any_hit(const BvhView& bvh, V3 org, V3 dir, float tmin, float t
       const uint32_t node = G.x + (uint32_t)popc32(G.y & 0xffu & ((1u << slot) - 1u));
       if (G.y & 0xff000000u) stack[sp++] = G;
       uint32_t cb, pb, im;
-      const uint32_t hm = intersect_node8(bvh.nodes, node, r, nc, &cb, &pb, &im);
+      const uint32_t hm = node_test<true, H2>(bvh.nodes, node, r, nc, &cb, &pb, &im);
       if (STATS) cnt->nodes++;
       G.x = cb; G.y = (hm & 0xff000000u) | im;
       T.x = pb; T.y = hm & 0x00ffffffu;

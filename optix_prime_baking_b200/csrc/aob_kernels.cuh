@@ -189,7 +189,7 @@ __global__ void k_gather_tris(const F4* __restrict__ soup, const uint32_t* __res
 __global__ void k_empty_node(Node8* nd) {
   Node8 n;
   memset(&n, 0, sizeof(n));
-  for (int k = 0; k < 8; k++) { n.qlox[k] = n.qloy[k] = n.qloz[k] = 255; }
+  for (int k = 0; k < 8; k++) for (int a = 0; a < 3; a++) n.q[a][k][0] = 255;
   *nd = n;
 }
 
@@ -441,16 +441,33 @@ constexpr int kAoBlock = 128;
 #endif
 constexpr int kSmStack = AOB_SM_STACK;
 
-template <bool STATS, bool TWO_LEVEL, bool CLAMP_TMAX>
+// Rays the packed-fp16 node test cannot take (a direction component below 2^-12 in the space being
+// traversed: ~5 in 10^4) are not traced by the fused kernel: it appends (sample, stratum) to `list`
+// and k_ao_deferred traces them afterwards with the fp32 test.  count > capacity means entries were
+// dropped; the host then repeats the launch with the fp32 kernels.
+struct DeferredRays {
+  U2* list;            // (sample index relative to `begin`, stratum)
+  uint32_t* count;
+  uint32_t capacity;
+};
+AOB_D void defer_ray(const DeferredRays& D, uint32_t rel, uint32_t pass) {
+  const uint32_t i = atomicAdd(D.count, 1u);
+  if (i < D.capacity) { U2 e; e.x = rel; e.y = pass; D.list[i] = e; }
+}
+
+template <bool STATS, bool TWO_LEVEL, bool CLAMP_TMAX, bool H2>
 __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleView S, uint64_t begin, uint32_t n, int q, float offset,
                                                              float maxdist, uint32_t n_chunks, uint32_t refill_below,
                                                              uint32_t part, uint32_t num_parts, uint32_t sb_blocks, uint32_t n_local_blocks,
                                                              uint32_t* __restrict__ hits, unsigned long long* __restrict__ counter,
-                                                             unsigned long long* __restrict__ stats) {
+                                                             unsigned long long* __restrict__ stats, DeferredRays deferred) {
 #if AOB_SM_STACK > 0
   __shared__ U2 s_stack[kSmStack][kAoBlock];
 #endif
   U2 l_stack[kStackSize - kSmStack];
+  // The fp16 test is used for flattened scenes only: under a TLAS it measured slower than fp32 (config 4:
+  // 3.98 vs 4.23 Grays/s), and object-space rays of scaled instances are not unit length.
+  static_assert(!(H2 && TWO_LEVEL), "the packed-fp16 node test is instantiated for flattened scenes only");
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t lt_mask = (1u << lane) - 1u;
   const uint32_t q2 = (uint32_t)(q * q);
@@ -485,7 +502,7 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
   // per-lane ray state
   RayState r;
   r.tmin = 0.0f; r.tmax = maxdist;
-  r.org = org; r.dir = org; r.idir = org;
+  r.org = org; r.dir = org; r.idir = org; r.wide = false;
   V3 wdir = v3(0, 0, 0);  // world-space direction (two-level: restored after a BLAS)
   bool in_blas = !TWO_LEVEL;
   U2 G;
@@ -563,10 +580,15 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
     // traversal loop starts its queued ray at once, without a refill.
     if (have_item && !la_valid && pass < pass_end) {
       const V3 d = ao_ray_dir((uint32_t)(begin + rel), pass, q, nrm, fnrm, onb);
+      const V3 id = v3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
+      if (H2 && !(fmaxf(fmaxf(fabsf(id.x), fabsf(id.y)), fabsf(id.z)) <= kH2MaxIdir)) {
+        defer_ray(deferred, rel, pass);   // world rays are unit length: only the reciprocal can disqualify them
+      } else {
+        s_la[0][threadIdx.x] = d.x; s_la[1][threadIdx.x] = d.y; s_la[2][threadIdx.x] = d.z;
+        s_la[3][threadIdx.x] = id.x; s_la[4][threadIdx.x] = id.y; s_la[5][threadIdx.x] = id.z;
+        la_valid = true;
+      }
       pass++;
-      s_la[0][threadIdx.x] = d.x; s_la[1][threadIdx.x] = d.y; s_la[2][threadIdx.x] = d.z;
-      s_la[3][threadIdx.x] = safe_rcp(d.x); s_la[4][threadIdx.x] = safe_rcp(d.y); s_la[5][threadIdx.x] = safe_rcp(d.z);
-      la_valid = true;
     }
     if (!ray_active && la_valid) start_queued();
     if (!__any_sync(0xffffffffu, ray_active)) {
@@ -586,7 +608,7 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
           const uint32_t node = G.x + (uint32_t)__popc(G.y & 0xffu & ((1u << slot) - 1u));
           if (G.y & 0xff000000u) push(sp, G);
           uint32_t cb, pb, im;
-          const uint32_t hm = intersect_node8<CLAMP_TMAX>(bvh.nodes, node, r, nc, &cb, &pb, &im);
+          const uint32_t hm = H2 ? intersect_node8_h2(bvh.nodes, node, r, &cb, &pb, &im) : intersect_node8<CLAMP_TMAX>(bvh.nodes, node, r, nc, &cb, &pb, &im);
           if (STATS) c_nodes++;
           G.x = cb; G.y = (hm & 0xff000000u) | im;
           T.x = pb; T.y = hm & 0x00ffffffu;
@@ -662,6 +684,25 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
     atomicAdd(&stats[0], (unsigned long long)c_nodes);
     atomicAdd(&stats[1], (unsigned long long)c_tris);
     atomicAdd(&stats[2], (unsigned long long)c_insts);
+  }
+}
+
+// The rays k_ao_persistent<.., H2 = true> set aside, traced with the fp32 node test; runs after it on
+// the same stream and adds to the same hit counters.
+__global__ void __launch_bounds__(128) k_ao_deferred(BvhView bvh, SampleView S, uint64_t begin, int q, float offset, float maxdist,
+                                                     DeferredRays D, uint32_t* __restrict__ hits) {
+  const uint32_t count = *D.count;
+  const uint32_t n = count < D.capacity ? count : D.capacity;
+  U2 stack[kStackSize];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const U2 e = D.list[i];
+    const uint64_t g = begin + e.x;
+    const V3 p = v3(S.pos[3 * g], S.pos[3 * g + 1], S.pos[3 * g + 2]);
+    const V3 nrm = v3(S.nrm[3 * g], S.nrm[3 * g + 1], S.nrm[3 * g + 2]);
+    const V3 fnrm = v3(S.fnrm[3 * g], S.fnrm[3 * g + 1], S.fnrm[3 * g + 2]);
+    const Onb onb = make_onb(nrm);
+    const V3 d = ao_ray_dir((uint32_t)g, e.y, q, nrm, fnrm, onb);
+    if (trace_any_hit<false, false>(bvh, ao_ray_origin(p, nrm, offset), d, 0.0f, maxdist, stack, nullptr)) atomicAdd(&hits[e.x], 1u);
   }
 }
 

@@ -167,6 +167,8 @@ struct AoBake {
   DBuf<uint32_t> d_hits;
   DBuf<unsigned long long> d_stats;
   DBuf<unsigned long long> d_counter;
+  DBuf<U2> d_deferred;               // rays the fp16 node test set aside (k_ao_deferred)
+  DBuf<uint32_t> d_deferred_count;
   bool have_ao = false;
   bool have_infos = false;           // sample_infos (tri_idx, bary, dA) are resident — needed by the vertex maps
 
@@ -398,6 +400,7 @@ int aobake_default_params(AoBakeParams* p) {
   p->collect_stats = 0;
   p->refill_below = 0;
   p->leaf_tris = 0;
+  p->node_test = 0;
   return AOBAKE_OK;
 }
 
@@ -436,7 +439,7 @@ int aobake_create(const AoBakeParams* params, AoBake** out) {
   }
   if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess || ((g_alloc_stream = ctx->own_stream), false) ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
-      ctx->d_stats.alloc(4) != cudaSuccess || ctx->d_counter.alloc(1) != cudaSuccess) {
+      ctx->d_stats.alloc(4) != cudaSuccess || ctx->d_counter.alloc(1) != cudaSuccess || ctx->d_deferred_count.alloc(1) != cudaSuccess) {
     g_create_error = std::string("context setup: ") + cudaGetErrorString(cudaGetLastError());
     delete ctx;
     return AOBAKE_ERR_CUDA;
@@ -891,7 +894,7 @@ int aobake_set_samples(AoBake* ctx, const AoSamples* s, const size_t* per_instan
 size_t aobake_num_samples(const AoBake* ctx) { return ctx ? ctx->num_samples : 0; }
 
 static int compute_ao_impl(AoBake* ctx, size_t begin, size_t end, int rays_per_sample, float offset, float maxdist, float* host_ao,
-                           uint32_t part, uint32_t num_parts, uint32_t block_samples) {
+                           uint32_t part, uint32_t num_parts, uint32_t block_samples, bool force_fp32 = false) {
   if (!ctx) return AOBAKE_ERR_INVALID_ARGUMENT;
   if (!ctx->have_scene) return ctx->fail(AOBAKE_ERR_STATE, "compute_ao before set_scene");
   if (begin > end || end > ctx->num_samples) return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "sample range [%zu,%zu) outside [0,%llu)", begin, end, (unsigned long long)ctx->num_samples);
@@ -937,6 +940,7 @@ static int compute_ao_impl(AoBake* ctx, size_t begin, size_t end, int rays_per_s
   CK(cudaEventRecord(ctx->ev0, st));
   const uint32_t q2 = (uint32_t)(q * q);
   int launches = 0;
+  bool use_h2 = false;
   // trace_kernel: 0 = auto (persistent, except for launches too small to amortise its work
   // distribution: < 32 M rays), 1 = simple, 2 = persistent
   const bool use_simple = num_parts == 1 && (ctx->params.trace_kernel == 1 || (ctx->params.trace_kernel == 0 && n * (uint64_t)q2 < (32ull << 20)));
@@ -959,16 +963,21 @@ static int compute_ao_impl(AoBake* ctx, size_t begin, size_t end, int rays_per_s
     // persistent variant: one resident wave of CTAs (a multiple of the SM count), dynamic work fetch
     if (n > 0xfffffff0ull) return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "more than 2^32 samples in one range");
     using KernelT = void (*)(BvhView, SampleView, uint64_t, uint32_t, int, float, float, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t,
-                             uint32_t, uint32_t*, unsigned long long*, unsigned long long*);
-    // the far clamp of the node test is only needed when maxdist can actually cull inside the scene
+                             uint32_t, uint32_t*, unsigned long long*, unsigned long long*, DeferredRays);
+    // node test: packed fp16 (two planes per instruction) for flattened scenes, unless asked otherwise
+    // or a previous attempt overflowed the deferred-ray list; fp32 under a TLAS (measured faster there)
+    use_h2 = AOB_H2 != 0 && !force_fp32 && ctx->params.node_test != 1 && !ctx->two_level;
+    // the far clamp of the fp32 node test is only needed when maxdist can actually cull inside the scene
     const bool clamp = !(maxdist > 1.01f * ctx->scene_diag + fabsf(offset));
     KernelT kern;
-    if (clamp)
-      kern = ctx->two_level ? (stats ? (KernelT)k_ao_persistent<true, true, true> : (KernelT)k_ao_persistent<false, true, true>)
-                            : (stats ? (KernelT)k_ao_persistent<true, false, true> : (KernelT)k_ao_persistent<false, false, true>);
+    if (use_h2)
+      kern = stats ? (KernelT)k_ao_persistent<true, false, false, true> : (KernelT)k_ao_persistent<false, false, false, true>;
+    else if (clamp)
+      kern = ctx->two_level ? (stats ? (KernelT)k_ao_persistent<true, true, true, false> : (KernelT)k_ao_persistent<false, true, true, false>)
+                            : (stats ? (KernelT)k_ao_persistent<true, false, true, false> : (KernelT)k_ao_persistent<false, false, true, false>);
     else
-      kern = ctx->two_level ? (stats ? (KernelT)k_ao_persistent<true, true, false> : (KernelT)k_ao_persistent<false, true, false>)
-                            : (stats ? (KernelT)k_ao_persistent<true, false, false> : (KernelT)k_ao_persistent<false, false, false>);
+      kern = ctx->two_level ? (stats ? (KernelT)k_ao_persistent<true, true, false, false> : (KernelT)k_ao_persistent<false, true, false, false>)
+                            : (stats ? (KernelT)k_ao_persistent<true, false, false, false> : (KernelT)k_ao_persistent<false, false, false, false>);
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kAoBlock, 0));
     if (per_sm < 1) per_sm = 1;
@@ -980,19 +989,37 @@ static int compute_ao_impl(AoBake* ctx, size_t begin, size_t end, int rays_per_s
     if ((uint64_t)grid * kAoBlock > items) grid = (unsigned)((items + kAoBlock - 1) / kAoBlock);
     if (n_chunks > 1 && num_parts == 1) CK(cudaMemsetAsync(ctx->d_hits.p + begin, 0, n * sizeof(uint32_t), st));
     CK(cudaMemsetAsync(ctx->d_counter.p, 0, sizeof(unsigned long long), st));
+    DeferredRays deferred{nullptr, nullptr, 0u};
+    if (use_h2) {
+      // expected: ~7e-4 of the rays; room for 1/128
+      const uint64_t want = std::min<uint64_t>(std::max<uint64_t>(owned_samples * q2 / 128ull, 1ull << 18), 1ull << 28);
+      if (ctx->d_deferred.n < want) CK(ctx->d_deferred.alloc(want));
+      CK(cudaMemsetAsync(ctx->d_deferred_count.p, 0, sizeof(uint32_t), st));
+      deferred.list = ctx->d_deferred.p; deferred.count = ctx->d_deferred_count.p; deferred.capacity = (uint32_t)ctx->d_deferred.n;
+    }
     const uint32_t refill = ctx->params.refill_below > 0 ? (uint32_t)ctx->params.refill_below : 28u;
     kern<<<grid, kAoBlock, 0, st>>>(bvh, S, (uint64_t)begin, (uint32_t)n, q, offset, maxdist, n_chunks, refill, part, num_parts, sb_blocks,
-                                    (uint32_t)n_local_blocks, ctx->d_hits.p + begin, ctx->d_counter.p, ctx->d_stats.p);
+                                    (uint32_t)n_local_blocks, ctx->d_hits.p + begin, ctx->d_counter.p, ctx->d_stats.p, deferred);
     CKL();
     launches++;
+    if (use_h2) {
+      k_ao_deferred<<<(unsigned)ctx->sm_count * 4u, 128, 0, st>>>(bvh, S, (uint64_t)begin, q, offset, maxdist, deferred, ctx->d_hits.p + begin);
+      CKL();
+      launches++;
+    }
   }
   k_ao_finalize<<<grid_for(n, 256), 256, 0, st>>>(ctx->d_hits.p + begin, n, (float)(q * q), ctx->d_ao.p + begin, part, num_parts, sb_blocks * 32u);
   CKL();
   launches++;
   ctx->timings.kernel_launches = launches;
   CK(cudaEventRecord(ctx->ev1, st));
+  uint32_t n_deferred = 0;
+  if (use_h2) CK(cudaMemcpyAsync(&n_deferred, ctx->d_deferred_count.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   if (host_ao) CK(cudaMemcpyAsync(host_ao, ctx->d_ao.p + begin, n * sizeof(float), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  if (use_h2 && n_deferred > ctx->d_deferred.n)   // entries were dropped: this result is incomplete, trace again in fp32
+    return compute_ao_impl(ctx, begin, end, rays_per_sample, offset, maxdist, host_ao, part, num_parts, block_samples, true);
+  ctx->stats.reserved[2] = (int32_t)std::min<uint32_t>(n_deferred, 0x7fffffffu);
   CK(cudaEventElapsedTime(&ctx->timings.trace_ms, ctx->ev0, ctx->ev1));
   if (stats) {
     unsigned long long hs[4];

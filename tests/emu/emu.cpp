@@ -13,6 +13,7 @@
 
 using namespace aob;
 
+static int g_node_test_fp32 = 0;              // 1: fp32 node test for every ray (cross-check of the fp16 test)
 static uint32_t g_max_leaf_override = 0;   // experiments: leaf slot capacity (0 = builder default)
 
 struct EmuBvh {
@@ -33,7 +34,7 @@ static uint32_t build_segment(const std::vector<F4>& plo, const std::vector<F4>&
   if (n == 0) {
     Node8 nd;
     memset(&nd, 0, sizeof(nd));
-    for (int k = 0; k < 8; k++) { nd.qlox[k] = nd.qloy[k] = nd.qloz[k] = 255; }
+    for (int k = 0; k < 8; k++) for (int a = 0; a < 3; a++) nd.q[a][k][0] = 255;
     nodes.push_back(nd);
     return node_offset;
   }
@@ -178,6 +179,7 @@ void* emu_bvh_create_two_level(uint32_t num_meshes, const float* const* mesh_tri
 }
 
 void emu_set_max_leaf(uint32_t m) { g_max_leaf_override = m; }
+void emu_set_node_test_fp32(int on) { g_node_test_fp32 = on; }
 void emu_bvh_destroy(void* h) { delete static_cast<EmuBvh*>(h); }
 uint64_t emu_bvh_num_nodes(void* h) { return static_cast<EmuBvh*>(h)->nodes.size(); }
 
@@ -195,7 +197,8 @@ uint64_t emu_trace(void* h, const float* rays, uint64_t n, uint8_t* hit, uint64_
     const float* p = rays + 8 * i;
     U2 stack[kStackSize];
     TraceCounters c = {0, 0, 0};
-    hit[i] = trace_any_hit<true>(v, v3(p[0], p[1], p[2]), v3(p[4], p[5], p[6]), p[3], p[7], stack, &c) ? 1 : 0;
+    hit[i] = (g_node_test_fp32 ? trace_any_hit<true, false>(v, v3(p[0], p[1], p[2]), v3(p[4], p[5], p[6]), p[3], p[7], stack, &c)
+                               : trace_any_hit<true, true>(v, v3(p[0], p[1], p[2]), v3(p[4], p[5], p[6]), p[3], p[7], stack, &c)) ? 1 : 0;
     nodes += c.nodes; tris += c.tris;
   }
   if (tri_tests) *tri_tests = tris;

@@ -169,6 +169,49 @@ def test_compute_ao_and_vertex_maps(api, name, trace_kernel):
         assert np.abs(v_ls[i] - o_ls[i]).max() <= VERTEX_AO_TOL
 
 
+@pytest.mark.parametrize("name", ["sphere_ground", "heightfield"])
+def test_fp16_and_fp32_node_tests_give_identical_hit_counts(api, name):
+    """Both box tests are conservative and the triangle test decides, so the per-sample hit counts of
+    the fused kernel must not depend on which one ran — including the rays the fp16 test hands to the
+    deferred fp32 launch (axis-parallel directions are forced here by axis-aligned normals)."""
+    scene, blockers = SCENES[name]
+    off, maxd = scenes.default_distances(scene)
+    rays = 256
+    res = []
+    for node_test in (0, 1):
+        with api.Baker(trace_kernel=2, node_test=node_test) as bk:
+            bk.set_scene(scene, blockers)
+            total, per = bk.distribute_samples(1, 0)
+            bk.sample_instances(per, 1, download=False)
+            bk.compute_ao(rays, off, maxd, download=False)
+            res.append((bk.hit_counts(), bk.stats().reserved[2]))
+    assert np.array_equal(res[0][0], res[1][0])
+    assert res[0][1] > 0 and res[1][1] == 0          # the fp16 build did defer some rays, the fp32 build none
+
+
+def test_scaled_instances_under_a_tlas(api):
+    """Non-rigid instance transforms: object-space rays are not unit length (the one-ray-per-thread
+    kernels then take the fp32 box test per ray; the fused two-level kernel is fp32 throughout)."""
+    base, _ = scenes.config4_instanced(grid=2, stacks=12, slices=12, with_ground=False)
+    insts = []
+    for k, inst in enumerate(base.instances):
+        xf = inst.xform.copy()
+        xf[:3, :3] = xf[:3, :3] @ np.diag([1.0 + 0.3 * k, 1.0, 0.5]).astype(np.float32)    # non-uniform scale
+        insts.append(Instance(inst.mesh_index, xf))
+    scene = Scene(base.meshes, insts)
+    off, maxd = scenes.default_distances(scene)
+    orc = Oracle(scene, None, 2)
+    for trace_kernel in (1, 2):
+        with api.Baker(trace_kernel=trace_kernel, instancing_mode=api.INSTANCING_TWO_LEVEL) as bk:
+            bk.set_scene(scene)
+            total, per = bk.distribute_samples(2, 0)
+            sb = bk.sample_instances(per, 2)
+            bk.compute_ao(64, off, maxd, download=False)
+            hits = bk.hit_counts()
+        _, ohits = orc.compute_ao(sb, 64, off, maxd)
+        assert 1.0 - np.abs(hits.astype(np.int64) - ohits.astype(np.int64)).sum() / (total * 64) >= HIT_AGREEMENT
+
+
 def test_analytic_sphere_over_plane(api):
     """Known answer, no oracle: a convex body over an (effectively) infinite plane has
     AO(n) = (1 + n.up) / 2."""
