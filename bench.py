@@ -399,7 +399,7 @@ def main():
                          "kernel_ms": kms, "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray,
                          "tris_per_ray": tris_per_ray, "instances_per_ray": insts_per_ray,
                          "note": "algorithmic bytes = 80 B/node visit + 48 B/triangle test + 80 B/instance entry + 40 B/sample "
-                                 "(SURVEY §8d); traversal is latency/L2 bound, see DESIGN.md"},
+                                 "(SURVEY §8d); served by L1/L2 — the kernel is instruction-issue bound, see DESIGN.md §4.1"},
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))

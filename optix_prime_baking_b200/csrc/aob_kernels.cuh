@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
   bool have_item = false, ray_active = false, exhausted = false;
   uint32_t rel = 0, pass = 0, pass_end = 0, nh = 0;
   uint32_t supply_next = 0, supply_left = 0, supply_chunk = 0;  // warp-uniform
-  V3 org = v3(0, 0, 0), nrm = v3(0, 0, 0), fnrm = v3(0, 0, 0);
+  V3 org = v3(0, 0, 0);   // the normals are re-read per generated ray (L1): 6 registers matter more
   Onb onb;
   onb.t = onb.b = v3(0, 0, 0);
   // per-lane ray state
@@ -563,8 +563,7 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
         pass_end = (uint32_t)(((uint64_t)(supply_chunk + 1) * q2) / n_chunks);
         const uint64_t g = begin + rel;
         const V3 p = v3(S.pos[3 * g], S.pos[3 * g + 1], S.pos[3 * g + 2]);
-        nrm = v3(S.nrm[3 * g], S.nrm[3 * g + 1], S.nrm[3 * g + 2]);
-        fnrm = v3(S.fnrm[3 * g], S.fnrm[3 * g + 1], S.fnrm[3 * g + 2]);
+        const V3 nrm = v3(S.nrm[3 * g], S.nrm[3 * g + 1], S.nrm[3 * g + 2]);
         onb = make_onb(nrm);
         org = ao_ray_origin(p, nrm, offset);
         nh = 0;
@@ -579,6 +578,9 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
     // warp converged instead of only the few idle lanes; a lane whose ray ends inside the
     // traversal loop starts its queued ray at once, without a refill.
     if (have_item && !la_valid && pass < pass_end) {
+      const uint64_t gf = 3ull * (begin + rel);
+      const V3 fnrm = v3(__ldg(S.fnrm + gf), __ldg(S.fnrm + gf + 1), __ldg(S.fnrm + gf + 2));
+      const V3 nrm = v3(__ldg(S.nrm + gf), __ldg(S.nrm + gf + 1), __ldg(S.nrm + gf + 2));
       const V3 d = ao_ray_dir((uint32_t)(begin + rel), pass, q, nrm, fnrm, onb);
       const V3 id = v3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
       if (H2 && !(fmaxf(fmaxf(fabsf(id.x), fabsf(id.y)), fabsf(id.z)) <= kH2MaxIdir)) {
