@@ -119,7 +119,9 @@ typedef struct AoBakeParams {
   int32_t leaf_tris;              /* triangles per leaf slot of the 8-wide BVH, 1..3 (0 = default: 2 flattened, 1 per BLAS) */
   int32_t node_test;              /* box test of the fused kernel: 0 = auto (packed fp16, two planes per instruction; the few
                                      rays outside its range are traced by a second small launch in fp32), 1 = fp32 only */
-  int32_t reserved[5];
+  int32_t deferred_capacity;      /* entries of the deferred-ray list (0 = auto: 1/128 of a launch's rays); an overflow makes
+                                     aobake_compute_ao repeat the launch with the fp32 kernels — settable so that tests can force it */
+  int32_t reserved[4];
 } AoBakeParams;
 
 typedef struct AoTimings {        /* milliseconds, device-timed with CUDA events unless noted */
@@ -145,7 +147,8 @@ typedef struct AoStats {
   uint64_t instance_entries;
   uint64_t rays;
   int32_t two_level;
-  int32_t reserved[7];            /* [0] = depth of the top-level 8-wide tree, [1] = deepest BLAS (two-level) */
+  int32_t reserved[7];            /* [0] = depth of the top-level 8-wide tree, [1] = deepest BLAS (two-level),
+                                     [2] = rays the last compute_ao handed to the deferred fp32 launch */
 } AoStats;
 
 typedef struct AoBake AoBake;

@@ -38,7 +38,7 @@ EXPORTS = [
 class AoBakeParams(C.Structure):
     _fields_ = [("device", C.c_int32), ("instancing_mode", C.c_int32), ("cg_max_iterations", C.c_int32),
                 ("cg_tolerance", C.c_float), ("trace_kernel", C.c_int32), ("collect_stats", C.c_int32),
-                ("refill_below", C.c_int32), ("leaf_tris", C.c_int32), ("node_test", C.c_int32), ("reserved", C.c_int32 * 5)]
+                ("refill_below", C.c_int32), ("leaf_tris", C.c_int32), ("node_test", C.c_int32), ("deferred_capacity", C.c_int32), ("reserved", C.c_int32 * 4)]
 
 
 class AoTimings(C.Structure):
@@ -119,7 +119,7 @@ class Baker:
 
     def __init__(self, device: int = 0, instancing_mode: int = INSTANCING_AUTO, collect_stats: bool = False,
                  cg_tolerance: float = 1e-6, cg_max_iterations: int = 2000, trace_kernel: int = 0,
-                 refill_below: int = 0, leaf_tris: int = 0, node_test: int = 0):
+                 refill_below: int = 0, leaf_tris: int = 0, node_test: int = 0, deferred_capacity: int = 0):
         self.lib = load_library()
         p = default_params()
         p.device, p.instancing_mode, p.collect_stats = device, instancing_mode, int(collect_stats)
@@ -127,6 +127,7 @@ class Baker:
         p.refill_below = refill_below
         p.leaf_tris = leaf_tris
         p.node_test = node_test
+        p.deferred_capacity = deferred_capacity
         self.device = device
         self._h = C.c_void_p()
         rc = self.lib.aobake_create(C.byref(p), C.byref(self._h))

@@ -401,6 +401,7 @@ int aobake_default_params(AoBakeParams* p) {
   p->refill_below = 0;
   p->leaf_tris = 0;
   p->node_test = 0;
+  p->deferred_capacity = 0;
   return AOBAKE_OK;
 }
 
@@ -992,8 +993,10 @@ static int compute_ao_impl(AoBake* ctx, size_t begin, size_t end, int rays_per_s
     DeferredRays deferred{nullptr, nullptr, 0u};
     if (use_h2) {
       // expected: ~7e-4 of the rays; room for 1/128
-      const uint64_t want = std::min<uint64_t>(std::max<uint64_t>(owned_samples * q2 / 128ull, 1ull << 18), 1ull << 28);
-      if (ctx->d_deferred.n < want) CK(ctx->d_deferred.alloc(want));
+      const uint64_t want = ctx->params.deferred_capacity > 0
+                                ? (uint64_t)ctx->params.deferred_capacity
+                                : std::min<uint64_t>(std::max<uint64_t>(owned_samples * q2 / 128ull, 1ull << 18), 1ull << 28);
+      if (ctx->d_deferred.n < want || ctx->params.deferred_capacity > 0) CK(ctx->d_deferred.alloc(want));
       CK(cudaMemsetAsync(ctx->d_deferred_count.p, 0, sizeof(uint32_t), st));
       deferred.list = ctx->d_deferred.p; deferred.count = ctx->d_deferred_count.p; deferred.capacity = (uint32_t)ctx->d_deferred.n;
     }

@@ -187,6 +187,13 @@ def test_fp16_and_fp32_node_tests_give_identical_hit_counts(api, name):
             res.append((bk.hit_counts(), bk.stats().reserved[2]))
     assert np.array_equal(res[0][0], res[1][0])
     assert res[0][1] > 0 and res[1][1] == 0          # the fp16 build did defer some rays, the fp32 build none
+    # a deferred-ray list that is too small must not lose rays: the launch is repeated in fp32
+    with api.Baker(trace_kernel=2, deferred_capacity=4) as bk:
+        bk.set_scene(scene, blockers)
+        total, per = bk.distribute_samples(1, 0)
+        bk.sample_instances(per, 1, download=False)
+        bk.compute_ao(rays, off, maxd, download=False)
+        assert np.array_equal(bk.hit_counts(), res[0][0])
 
 
 def test_scaled_instances_under_a_tlas(api):
