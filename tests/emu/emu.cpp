@@ -221,6 +221,27 @@ int emu_woop_variants_agree(const float* rays, uint64_t n, const float* tris9, u
   return bad;
 }
 
+// ---- the two box tests in isolation (property tests: conservative against an exact fp64 slab test) ----
+// node80: one Node8 record; rays: n x (o.xyz, tmin, d.xyz, tmax); variant 0 = packed fp16, 1 = fp32.
+// masks[i] = traversal mask of ray i ([31:24] internal slots | [23:0] leaf primitive bits).
+void emu_node_test(const void* node80, const float* rays, uint64_t n, int variant, uint32_t* masks, uint8_t* wide) {
+  const U4* nodes = reinterpret_cast<const U4*>(node80);
+  const NodeConsts nc = make_node_consts();
+  for (uint64_t i = 0; i < n; i++) {
+    const float* p = rays + 8 * i;
+    RayState r;
+    ray_setup(r, v3(p[0], p[1], p[2]), v3(p[4], p[5], p[6]), p[3], p[7]);
+    uint32_t cb, pb, im;
+    wide[i] = r.wide ? 1 : 0;
+    masks[i] = variant == 0 ? intersect_node8_h2(nodes, 0, r, &cb, &pb, &im) : intersect_node8<true>(nodes, 0, r, nc, &cb, &pb, &im);
+  }
+}
+// fp16 emulation shims against an independent implementation (numpy float16) in the tests
+uint32_t emu_h2_pack_sat(float hi, float lo) { return h2_pack_sat(hi, lo); }
+uint32_t emu_h2_fma(uint32_t a, uint32_t b, uint32_t c) { return h2_fma(a, b, c); }
+uint32_t emu_h2_min(uint32_t a, uint32_t b) { return h2_min(a, b); }
+uint32_t emu_h2_lane_sum(uint32_t a) { return h2_lane_sum(a); }
+
 // ---- math parity hooks ----
 uint32_t emu_tea(uint32_t rounds, uint32_t v0, uint32_t v1) {
   switch (rounds) { case 2: return tea<2>(v0, v1); case 4: return tea<4>(v0, v1); case 16: return tea<16>(v0, v1); default: return 0; }
