@@ -133,31 +133,44 @@ def use_all_host_cores():
     return n
 
 
-def cpu_baseline(scene, blockers, samples, rays, off, maxd, target_rays=12_000_000):
-    """The oracle (kind 'port': the reference cannot be compiled) on all host cores,
-    on a bounded, strided subset of the workload's samples."""
-    from tests.oracle_binding import Oracle, lib
+def strided_subset(samples, n_sub, shift=0):
     from optix_prime_baking_b200.ctypes_types import SampleBuffers
-    use_all_host_cores()
-    q = int(np.float32(np.sqrt(np.float32(rays))) + np.float32(0.5))
-    n_sub = max(1, min(samples.n, target_rays // (q * q)))
-    pick = np.linspace(0, samples.n - 1, n_sub).astype(np.int64)
+    pick = (np.linspace(0, samples.n - 1, n_sub).astype(np.int64) + shift) % samples.n
     sub = SampleBuffers(n_sub)
     sub.positions[...] = samples.positions[pick]
     sub.normals[...] = samples.normals[pick]
     sub.face_normals[...] = samples.face_normals[pick]
+    return sub
+
+
+def cpu_baseline(scene, blockers, samples, rays, off, maxd, pilot_rays=12_000_000, target_seconds=12.0):
+    """The oracle (kind 'port': the reference cannot be compiled) on all host cores, on a
+    bounded, evenly strided subset of the workload's samples: a short pilot sizes the timed sample
+    for about `target_seconds` of CPU work (the whole workload if that is less)."""
+    from tests.oracle_binding import Oracle, lib
+    use_all_host_cores()
+    q = int(np.float32(np.sqrt(np.float32(rays))) + np.float32(0.5))
     orc = Oracle(scene, blockers)
     t0 = time.perf_counter()
     _ = orc.tracer
     t_build = time.perf_counter() - t0
+    n_pilot = max(1, min(samples.n, pilot_rays // (q * q)))
+    pilot = strided_subset(samples, n_pilot)
+    dt_pilot = 1e9
+    for _ in range(2):   # the first call also pays thread start-up and page faults
+        t0 = time.perf_counter()
+        ao, hits = orc.compute_ao(pilot, rays, off, maxd)
+        dt_pilot = min(dt_pilot, time.perf_counter() - t0)
+    n_sub = int(max(n_pilot, min(samples.n, target_seconds * n_pilot / max(dt_pilot, 1e-6))))
+    sub = strided_subset(samples, n_sub, shift=1)
     t0 = time.perf_counter()
-    ao, hits = orc.compute_ao(sub, rays, off, maxd)
+    orc.compute_ao(sub, rays, off, maxd)
     dt = time.perf_counter() - t0
     cores = lib().ao_oracle_num_threads()
     orc.close()
     return {"value": n_sub * q * q / dt / 1e6, "unit": "Mrays/s", "cores": int(cores), "kind": "port",
-            "sample": f"{n_sub} evenly strided samples x {q * q} rays = {n_sub * q * q} rays of the same workload "
-                      f"(oracle BVH build {t_build:.1f} s excluded)", "seconds": dt}, sub, hits
+            "sample": f"{n_sub} evenly strided samples x {q * q} rays = {n_sub * q * q} rays of the same workload, {dt:.1f} s "
+                      f"(oracle BVH build {t_build:.1f} s excluded; sized by a {n_pilot * q * q}-ray pilot)", "seconds": dt}, pilot, hits
 
 
 def run_reference(args, rank, world):
@@ -174,16 +187,20 @@ def run_reference(args, rank, world):
     total, per = orc.distribute_samples(min_per, requested)
     samples = orc.sample_instances(per, min_per)
     q = int(np.float32(np.sqrt(np.float32(rays))) + np.float32(0.5))
-    n_sub = max(1, min(samples.n, 6_000_000 // (q * q)))
     _ = orc.tracer
-    from optix_prime_baking_b200.ctypes_types import SampleBuffers
+    # a step = one bounded sample of the workload, sized by a pilot for ~3 s of CPU work and so that
+    # the whole --steps/--warmup run stays within about two and a half minutes
+    n_pilot = max(1, min(samples.n, 6_000_000 // (q * q)))
+    dt_pilot = 1e9
+    for _ in range(2):   # the first call also pays thread start-up and page faults
+        t0 = time.perf_counter()
+        orc.compute_ao(strided_subset(samples, n_pilot), rays, off, maxd)
+        dt_pilot = min(dt_pilot, time.perf_counter() - t0)
+    per_step_s = min(3.0, 150.0 / max(1, args.warmup + args.steps))
+    n_sub = int(max(n_pilot, min(samples.n, per_step_s * n_pilot / max(dt_pilot, 1e-6))))
     times = []
     for s in range(args.warmup + args.steps):
-        pick = (np.linspace(0, samples.n - 1, n_sub).astype(np.int64) + s) % samples.n
-        sub = SampleBuffers(n_sub)
-        sub.positions[...] = samples.positions[pick]
-        sub.normals[...] = samples.normals[pick]
-        sub.face_normals[...] = samples.face_normals[pick]
+        sub = strided_subset(samples, n_sub, shift=s)
         t0 = time.perf_counter()
         orc.compute_ao(sub, rays, off, maxd)
         if s >= args.warmup:
@@ -191,7 +208,7 @@ def run_reference(args, rank, world):
     dt = float(np.mean(times))
     val = n_sub * q * q / dt / 1e6
     cores = int(lib().ao_oracle_num_threads())
-    sample = f"{n_sub} strided samples x {q * q} rays per step"
+    sample = f"{n_sub} evenly strided samples x {q * q} rays = {n_sub * q * q} rays per step ({dt:.2f} s)"
     print(json.dumps({
         "impl": "reference", "metric": "occlusion Mrays/s", "value": val, "unit": "Mrays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
