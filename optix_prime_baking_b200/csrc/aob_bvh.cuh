@@ -575,9 +575,6 @@ AOB_D uint32_t intersect_node8(const U4* nodes, uint32_t idx, const RayState& r,
 // that is > 65504 away from a hit (any hit has |B| < 1).  NaN can only arise as inf - inf in the
 // last add, i.e. for a box that is a miss anyway, and reads as a hit.  tests/emu checks this test
 // against brute force and against the fp32 test.
-#ifndef AOB_PADK
-#define AOB_PADK 1.0f
-#endif
 AOB_D uint32_t intersect_node8_h2(const U4* nodes, uint32_t idx, const RayState& r, uint32_t* child_base, uint32_t* prim_base,
                                   uint32_t* imask) {
   const U4* p = nodes + 5ull * idx;
@@ -595,10 +592,10 @@ AOB_D uint32_t intersect_node8_h2(const U4* nodes, uint32_t idx, const RayState&
   const float ux = r.idir.x * inv, uy = r.idir.y * inv, uz = r.idir.z * inv;
   const float ax = (sx * 16777216.0f) * ux, ay = (sy * 16777216.0f) * uy, az = (sz * 16777216.0f) * uz;
   const float bx = fmaf(dx, ux, -tcs), by = fmaf(dy, uy, -tcs), bz = fmaf(dz, uz, -tcs);
-  const float g = AOB_PADK * fmaf(5.0e-7f, fabsf(tcs), 6.5e-8f);
-  const float px = fmaf(AOB_PADK * 1.6e-8f, fabsf(ax), fmaf(AOB_PADK * 1.0e-3f, fabsf(bx), g));
-  const float py = fmaf(AOB_PADK * 1.6e-8f, fabsf(ay), fmaf(AOB_PADK * 1.0e-3f, fabsf(by), g));
-  const float pz = fmaf(AOB_PADK * 1.6e-8f, fabsf(az), fmaf(AOB_PADK * 1.0e-3f, fabsf(bz), g));
+  const float g = fmaf(5.0e-7f, fabsf(tcs), 6.5e-8f);
+  const float px = fmaf(1.6e-8f, fabsf(ax), fmaf(1.0e-3f, fabsf(bx), g));
+  const float py = fmaf(1.6e-8f, fabsf(ay), fmaf(1.0e-3f, fabsf(by), g));
+  const float pz = fmaf(1.6e-8f, fabsf(az), fmaf(1.0e-3f, fabsf(bz), g));
   // lanes: low = -(near plane), high = far plane
   const uint32_t A2x = h2_pack_sat(ax, -ax), A2y = h2_pack_sat(ay, -ay), A2z = h2_pack_sat(az, -az);
   const uint32_t B2x = h2_pack_sat(bx + px, px - bx), B2y = h2_pack_sat(by + py, py - by), B2z = h2_pack_sat(bz + pz, pz - bz);
