@@ -219,6 +219,33 @@ def test_scaled_instances_under_a_tlas(api):
         assert 1.0 - np.abs(hits.astype(np.int64) - ohits.astype(np.int64)).sum() / (total * 64) >= HIT_AGREEMENT
 
 
+def test_whole_bake_golden(api):
+    """The CUDA path against the committed fixture tests/golden/bake_golden.npz: bit-exact samples,
+    rays, hit counts and averaged vertex AO; least-squares vertex AO within 1e-5."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bake_golden.npz"))
+    scene, blockers = scenes.config1_sphere(8, 10)
+    off, maxd = scenes.default_distances(scene)
+    for trace_kernel in (1, 2):
+        with api.Baker(trace_kernel=trace_kernel) as bk:
+            bk.set_scene(scene, blockers)
+            total, per = bk.distribute_samples(2, 0)
+            sb = bk.sample_instances(per, 2)
+            assert np.array_equal(sb.infos["tri_idx"], g["tri_idx"])
+            for name, arr in [("bary", sb.infos["bary"]), ("dA", sb.infos["dA"]), ("positions", sb.positions), ("normals", sb.normals),
+                              ("face_normals", sb.face_normals)]:
+                assert np.array_equal(np.ascontiguousarray(arr).view(np.uint32), g[name]), name
+            assert np.array_equal(bk.dump_rays(0, 8, 16, off, maxd).view(np.uint32).reshape(g["rays_first8"].shape), g["rays_first8"])
+            ao = bk.compute_ao(16, off, maxd)
+            hits = bk.hit_counts()
+            same = hits == g["hits"]
+            assert np.abs(hits.astype(np.int64) - g["hits"].astype(np.int64)).sum() <= 1      # 4480 rays: at most one edge case
+            assert np.array_equal(ao[same].view(np.uint32), g["ao"][same])
+            bk.set_ao(g["ao"].view(np.float32))                                                # vertex maps of the golden AO
+            assert np.abs(bk.map_ao_to_vertices(api.FILTER_AREA_BASED)[0] - g["v_area"].view(np.float32)).max() < 1e-6
+            assert np.abs(bk.map_ao_to_vertices(api.FILTER_LEAST_SQUARES, 0.1)[0] - g["v_ls"]).max() < 1e-5
+
+
 def test_analytic_sphere_over_plane(api):
     """Known answer, no oracle: a convex body over an (effectively) infinite plane has
     AO(n) = (1 + n.up) / 2."""

@@ -54,6 +54,27 @@ def test_rng_golden(golden):
         assert np.float32(ob.halton(i, base)).view(np.uint32) == int(want, 16)
 
 
+def test_whole_bake_golden():
+    """A complete small bake (samples, rays, hit counts, vertex AO) against the committed fixture
+    tests/golden/bake_golden.npz (written by tests/golden/make_golden.py from the oracle)."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bake_golden.npz"))
+    scene, blockers = scenes.config1_sphere(8, 10)
+    orc = Oracle(scene, blockers)
+    total, per = orc.distribute_samples(2, 0)
+    sb = orc.sample_instances(per, 2)
+    off, maxd = scenes.default_distances(scene)
+    assert np.float32(off) == g["offset"] and np.float32(maxd) == g["maxdist"]
+    assert np.array_equal(sb.infos["tri_idx"], g["tri_idx"])
+    for name, arr in [("bary", sb.infos["bary"]), ("dA", sb.infos["dA"]), ("positions", sb.positions), ("normals", sb.normals),
+                      ("face_normals", sb.face_normals)]:
+        assert np.array_equal(np.ascontiguousarray(arr).view(np.uint32), g[name]), name
+    assert np.array_equal(orc.generate_rays(sb, 0, 8, 16, off, maxd).view(np.uint32), g["rays_first8"])
+    ao, hits = orc.compute_ao(sb, 16, off, maxd)
+    assert np.array_equal(hits, g["hits"]) and np.array_equal(ao.view(np.uint32), g["ao"])
+    assert np.array_equal(orc.filter_area(sb, ao)[0].view(np.uint32), g["v_area"])
+    assert np.abs(orc.filter_least_squares(sb, ao, 0.1, tol=1e-12)[0] - g["v_ls"]).max() < 1e-6
+
+
 def test_rng_properties():
     # lcg low 24 bits; rnd in [0,1); halton(1,2)=0.5, halton(2,2)=0.25, halton(1,3)=1/3
     assert all(0 <= x < (1 << 24) for x in ob.lcg_stream(12345, 1000))
