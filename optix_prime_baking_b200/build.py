@@ -36,12 +36,15 @@ def needs_build() -> bool:
     return any(os.path.getmtime(s) > t for s in sources())
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, out: str | None = None, extra_flags=()) -> str:
+    """Builds libaobake.so.  `out` + `extra_flags` build a variant elsewhere (kernel A/B runs load it
+    through the AOBAKE_LIB environment variable; see profiles/ab_variants.py)."""
+    if out is None and not force and not needs_build():
         return LIB_PATH
+    out = out or LIB_PATH
     host_cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    cmd = [_nvcc(), *NVCC_FLAGS, "-ccbin", host_cxx, "-I", os.path.join(ROOT, "include"), "-I", CSRC,
-           "-o", LIB_PATH, os.path.join(CSRC, "aobake.cu")]
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra_flags, "-ccbin", host_cxx, "-I", os.path.join(ROOT, "include"), "-I", CSRC,
+           "-o", out, os.path.join(CSRC, "aobake.cu")]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -49,7 +52,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return LIB_PATH
+    return out
 
 
 if __name__ == "__main__":
