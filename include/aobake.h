@@ -121,7 +121,9 @@ typedef struct AoBakeParams {
                                      rays outside its range are traced by a second small launch in fp32), 1 = fp32 only */
   int32_t deferred_capacity;      /* entries of the deferred-ray list (0 = auto: 1/128 of a launch's rays); an overflow makes
                                      aobake_compute_ao repeat the launch with the fp32 kernels — settable so that tests can force it */
-  int32_t reserved[4];
+  int32_t tri_batch;              /* fused kernel: lanes of a warp that must hold leaf hits before the warp runs its triangle
+                                     block (paused lanes take no node steps meanwhile); 1 = test at once, 0 = default */
+  int32_t reserved[3];
 } AoBakeParams;
 
 typedef struct AoTimings {        /* milliseconds, device-timed with CUDA events unless noted */
@@ -213,6 +215,17 @@ int aobake_comm_init(AoBake* ctx, int rank, int nranks, const void* id128);
 int aobake_comm_destroy(AoBake* ctx);
 int aobake_compute_ao_distributed(AoBake* ctx, int rays_per_sample, float scene_offset, float scene_maxdistance,
                                   float* host_ao);
+/* The host-buffer forms of aobake_set_scene / aobake_set_samples for N ranks that all hold the same
+ * host arrays (what bake::computeAO receives on every rank).  set_scene_distributed: rank r copies only
+ * slice r of every vertex / index array over its own PCIe link and one in-place ncclAllGather per
+ * array completes them over NVLink (N uploads of the whole scene become one); every rank then builds
+ * the same BVH.  set_samples_distributed: only the super-blocks of 65536 samples this rank traces in
+ * aobake_compute_ao_distributed are copied (positions / normals / face normals; sample_infos whole,
+ * the vertex maps need them); afterwards only aobake_compute_ao_distributed may trace.  With one
+ * rank both are the plain calls.  A rank that fails before a collective makes every rank return
+ * AOBAKE_ERR_COMM instead of leaving the others blocked. */
+int aobake_set_scene_distributed(AoBake* ctx, const AoScene* scene, const AoScene* blockers);
+int aobake_set_samples_distributed(AoBake* ctx, const AoSamples* host_samples, const size_t* per_instance);
 /* bake::mapAOToVertices across the ranks of aobake_comm_init: the per-instance systems are independent
  * (block diagonal), so each rank filters a contiguous share of the instances (balanced by vertex
  * count) and one ncclAllReduce over zero-padded arrays gathers the result; every rank receives the

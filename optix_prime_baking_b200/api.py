@@ -29,7 +29,8 @@ EXPORTS = [
     "aobake_default_params", "aobake_create", "aobake_destroy", "aobake_last_error", "aobake_set_stream",
     "aobake_synchronize", "aobake_set_scene", "aobake_distribute_samples", "aobake_sample_instances",
     "aobake_set_samples", "aobake_compute_ao", "aobake_compute_ao_range", "aobake_compute_ao_interleaved", "aobake_comm_unique_id",
-    "aobake_comm_init", "aobake_comm_destroy", "aobake_compute_ao_distributed", "aobake_map_ao_to_vertices_distributed", "aobake_get_ao_device", "aobake_set_ao",
+    "aobake_comm_init", "aobake_comm_destroy", "aobake_compute_ao_distributed", "aobake_map_ao_to_vertices_distributed",
+    "aobake_set_scene_distributed", "aobake_set_samples_distributed", "aobake_get_ao_device", "aobake_set_ao",
     "aobake_map_ao_to_vertices", "aobake_make_ground_plane", "aobake_trace_rays", "aobake_dump_rays",
     "aobake_get_hit_counts", "aobake_get_timings", "aobake_get_stats", "aobake_num_samples",
 ]
@@ -38,7 +39,7 @@ EXPORTS = [
 class AoBakeParams(C.Structure):
     _fields_ = [("device", C.c_int32), ("instancing_mode", C.c_int32), ("cg_max_iterations", C.c_int32),
                 ("cg_tolerance", C.c_float), ("trace_kernel", C.c_int32), ("collect_stats", C.c_int32),
-                ("refill_below", C.c_int32), ("leaf_tris", C.c_int32), ("node_test", C.c_int32), ("deferred_capacity", C.c_int32), ("reserved", C.c_int32 * 4)]
+                ("refill_below", C.c_int32), ("leaf_tris", C.c_int32), ("node_test", C.c_int32), ("deferred_capacity", C.c_int32), ("tri_batch", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 class AoTimings(C.Structure):
@@ -81,6 +82,9 @@ def load_library(path: Optional[str] = None):
     L.aobake_set_stream.argtypes = [vp, vp]
     L.aobake_synchronize.argtypes = [vp]
     L.aobake_set_scene.argtypes = [vp, vp, vp]
+    if hasattr(L, "aobake_set_scene_distributed"):   # (absent only from older builds loaded through AOBAKE_LIB for A/B timing)
+        L.aobake_set_scene_distributed.argtypes = [vp, vp, vp]
+        L.aobake_set_samples_distributed.argtypes = [vp, vp, vp]
     L.aobake_distribute_samples.argtypes = [vp, sz, sz, vp, C.POINTER(sz)]
     L.aobake_sample_instances.argtypes = [vp, vp, sz, vp]
     L.aobake_set_samples.argtypes = [vp, vp, vp]
@@ -119,7 +123,7 @@ class Baker:
 
     def __init__(self, device: int = 0, instancing_mode: int = INSTANCING_AUTO, collect_stats: bool = False,
                  cg_tolerance: float = 1e-6, cg_max_iterations: int = 2000, trace_kernel: int = 0,
-                 refill_below: int = 0, leaf_tris: int = 0, node_test: int = 0, deferred_capacity: int = 0):
+                 refill_below: int = 0, leaf_tris: int = 0, node_test: int = 0, deferred_capacity: int = 0, tri_batch: int = 0):
         self.lib = load_library()
         p = default_params()
         p.device, p.instancing_mode, p.collect_stats = device, instancing_mode, int(collect_stats)
@@ -128,6 +132,7 @@ class Baker:
         p.leaf_tris = leaf_tris
         p.node_test = node_test
         p.deferred_capacity = deferred_capacity
+        p.tri_batch = tri_batch
         self.device = device
         self._h = C.c_void_p()
         rc = self.lib.aobake_create(C.byref(p), C.byref(self._h))
@@ -166,10 +171,13 @@ class Baker:
         self._ck(self.lib.aobake_synchronize(self._h))
 
     # -- bake path --
-    def set_scene(self, scene: Scene, blockers: Optional[Scene] = None):
+    def set_scene(self, scene: Scene, blockers: Optional[Scene] = None, distributed: bool = False):
+        """distributed=True: every rank of comm_init holds the same host scene; each uploads 1/N of it and
+        NCCL all-gathers the rest (aobake_set_scene_distributed)."""
         ps = PackedScene(scene)
         pb = PackedScene(blockers) if blockers is not None and len(blockers.instances) else None
-        self._ck(self.lib.aobake_set_scene(self._h, ps.ref(), pb.ref() if pb else None))
+        fn = self.lib.aobake_set_scene_distributed if distributed else self.lib.aobake_set_scene
+        self._ck(fn(self._h, ps.ref(), pb.ref() if pb else None))
         self.scene = scene
         self.per_instance = None
 
@@ -189,12 +197,14 @@ class Baker:
         self.per_instance = np.array([int(x) for x in per_instance], dtype=np.uint64)
         return sb
 
-    def set_samples(self, samples: SampleBuffers, per_instance: Optional[Sequence[int]] = None):
+    def set_samples(self, samples: SampleBuffers, per_instance: Optional[Sequence[int]] = None, distributed: bool = False):
+        """distributed=True: upload only the super-blocks this rank traces in compute_ao_distributed."""
         per = None
         if per_instance is not None:
             per = (C.c_size_t * max(len(per_instance), 1))(*[int(x) for x in per_instance])
             self.per_instance = np.array([int(x) for x in per_instance], dtype=np.uint64)
-        self._ck(self.lib.aobake_set_samples(self._h, samples.ref(), per))
+        fn = self.lib.aobake_set_samples_distributed if distributed else self.lib.aobake_set_samples
+        self._ck(fn(self._h, samples.ref(), per))
 
     @property
     def num_samples(self) -> int:
@@ -236,9 +246,9 @@ class Baker:
         self._ck(self.lib.aobake_comm_destroy(self._h))
 
     def compute_ao_distributed(self, rays_per_sample: int, scene_offset: float, scene_maxdistance: float,
-                               download: bool = True) -> Optional[np.ndarray]:
+                               download: bool = True, out: Optional[np.ndarray] = None) -> Optional[np.ndarray]:
         """Interleaved partition over the ranks of comm_init + in-place ncclAllReduce, all native."""
-        ao = np.empty(self.num_samples, dtype=np.float32) if download else None
+        ao = (out if out is not None else np.empty(self.num_samples, dtype=np.float32)) if download else None
         self._ck(self.lib.aobake_compute_ao_distributed(self._h, rays_per_sample, float(scene_offset), float(scene_maxdistance),
                                                         ao.ctypes.data if ao is not None else None))
         return ao

@@ -354,12 +354,14 @@ __global__ void k_place_samples(const InstDesc* __restrict__ inst, uint32_t n_in
 // ---------------------------------------------------------------------------------------
 // Trace
 // ---------------------------------------------------------------------------------------
+// H2 = false (AoBakeParams::node_test = 1) compiles the fp32 node test only.
+template <bool H2>
 __global__ void k_trace_rays(BvhView bvh, const float* __restrict__ rays, uint64_t n, uint8_t* __restrict__ hit) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4 a = reinterpret_cast<const float4*>(rays)[2 * i], b = reinterpret_cast<const float4*>(rays)[2 * i + 1];
   U2 stack[kStackSize];
-  hit[i] = trace_any_hit<false>(bvh, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), a.w, b.w, stack, nullptr) ? 1 : 0;
+  hit[i] = trace_any_hit<false, H2>(bvh, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), a.w, b.w, stack, nullptr) ? 1 : 0;
 }
 
 struct SampleView {
@@ -384,9 +386,21 @@ __global__ void k_dump_rays(SampleView S, uint64_t begin, uint64_t end, int q, f
   r[1] = make_float4(d.x, d.y, d.z, maxdist);
 }
 
+// The packed-fp16 node test assumes unit-length world rays, i.e. unit-length shading normals
+// (cosine_dir builds the direction from n and an orthonormal pair derived from it).  Samples made by
+// k_place_samples are normalised; caller-provided ones (aobake_set_samples) are checked here and a
+// sample set with any other normal is traced with the fp32 test.
+__global__ void k_check_unit_normals(const float* __restrict__ nrm, uint64_t begin, uint64_t end, uint32_t* __restrict__ flag) {
+  const uint64_t g = begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= end) return;
+  const float x = nrm[3 * g], y = nrm[3 * g + 1], z = nrm[3 * g + 2];
+  const float d2 = x * x + y * y + z * z;
+  if (!(fabsf(d2 - 1.0f) <= 1.0e-4f)) *flag = 1u;
+}
+
 // Variant 1 (simple): one warp per (32-sample block, strata chunk); lane = sample; each lane
 // walks its strata sequentially with a private local-memory stack.
-template <bool STATS>
+template <bool STATS, bool H2>
 __global__ void __launch_bounds__(256) k_ao_simple(BvhView bvh, SampleView S, uint64_t begin, uint64_t end, int q, float offset,
                                                    float maxdist, uint32_t n_chunks, uint32_t* __restrict__ hits,
                                                    unsigned long long* __restrict__ stats) {
@@ -409,7 +423,7 @@ __global__ void __launch_bounds__(256) k_ao_simple(BvhView bvh, SampleView S, ui
   uint32_t h = 0;
   for (uint32_t pass = p0; pass < p1; pass++) {
     const V3 d = ao_ray_dir((uint32_t)g, pass, q, n, fn, onb);
-    h += trace_any_hit<STATS>(bvh, o, d, 0.0f, maxdist, stack, &cnt) ? 1u : 0u;
+    h += trace_any_hit<STATS, H2>(bvh, o, d, 0.0f, maxdist, stack, &cnt) ? 1u : 0u;
   }
   if (n_chunks > 1) atomicAdd(&hits[g - begin], h);
   else hits[g - begin] = h;
@@ -457,7 +471,7 @@ AOB_D void defer_ray(const DeferredRays& D, uint32_t rel, uint32_t pass) {
 
 template <bool STATS, bool TWO_LEVEL, bool CLAMP_TMAX, bool H2>
 __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleView S, uint64_t begin, uint32_t n, int q, float offset,
-                                                             float maxdist, uint32_t n_chunks, uint32_t refill_below,
+                                                             float maxdist, uint32_t n_chunks, uint32_t refill_below, uint32_t tri_batch,
                                                              uint32_t part, uint32_t num_parts, uint32_t sb_blocks, uint32_t n_local_blocks,
                                                              uint32_t* __restrict__ hits, unsigned long long* __restrict__ counter,
                                                              unsigned long long* __restrict__ stats, DeferredRays deferred) {
@@ -505,8 +519,10 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
   r.org = org; r.dir = org; r.idir = org; r.wide = false;
   V3 wdir = v3(0, 0, 0);  // world-space direction (two-level: restored after a BLAS)
   bool in_blas = !TWO_LEVEL;
-  U2 G;
+  U2 G, T;   // node group being walked; primitive group of the last node step (kept while the lane is paused)
   G.x = 0; G.y = 0;
+  T.x = 0; T.y = 0;
+  bool paused = false;   // the lane holds leaf hits (T) and waits for the warp's next triangle block
   int sp = 0;
   uint32_t c_nodes = 0, c_tris = 0, c_insts = 0;
   // Multi-GPU interleave: this launch owns the super-blocks sb (of sb_blocks 32-sample blocks) with
@@ -599,9 +615,17 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
     }
 
     // ------------------------------ traverse ------------------------------
+    // Triangle tests are batched across the warp.  A lane whose node test reports leaf hits does not
+    // test them at once: it PAUSES (keeps its primitive group T, takes no further node step), and the
+    // triangle block runs only when at least `tri_batch` lanes are paused or no lane can still take a
+    // node step.  Run in place, the block costs the warp ~200 instructions in EVERY iteration for the
+    // two or three lanes that happen to have reached a leaf in that iteration (30-40 % of all issued
+    // instructions on configs 3 and 4, profiles/r2/srcprof_base_*.txt); batched it runs every few
+    // iterations for `tri_batch` lanes.  Any-hit semantics are untouched: a paused ray does no
+    // speculative work and resumes (or ends) with the result of its own test.
     while (true) {
-      if (ray_active) {
-        U2 T;
+      bool hit = false;
+      if (ray_active && !paused) {
         T.x = 0; T.y = 0;
         if (G.y & 0xff000000u) {
           const int bit = 31 - __clz((int)G.y);
@@ -618,12 +642,9 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
           T = G;  // a postponed TLAS primitive group
           G.x = 0; G.y = 0;
         }
-        bool hit = false;
         if (T.y) {
           if (in_blas) {
-            uint32_t tested = 0;
-            hit = test_tri_group(bvh.tris, T.x, T.y, r.org, r.dir, 0.0f, maxdist, &tested);
-            if (STATS) c_tris += tested;
+            paused = true;
           } else if (TWO_LEVEL) {
             // instances of the group: skip those whose bounding sphere the world ray cannot touch,
             // enter the first one it can — save the TLAS continuation, switch to object space
@@ -650,9 +671,20 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
             }
           }
         }
-        // Ray end and restart are written once, straight-line: lanes ending on a hit, lanes ending
-        // on an empty stack and lanes that merely pop all run the same short sequence instead of
-        // three serialised divergent copies.
+      }
+      const uint32_t pm = __ballot_sync(0xffffffffu, paused);
+      if (pm != 0u && ((uint32_t)__popc(pm) >= tri_batch || pm == __ballot_sync(0xffffffffu, ray_active))) {
+        if (paused) {
+          uint32_t tested = 0;
+          hit = test_tri_group(bvh.tris, T.x, T.y, r.org, r.dir, 0.0f, maxdist, &tested);
+          if (STATS) c_tris += tested;
+          paused = false;
+        }
+      }
+      // Ray end and restart are written once, straight-line: lanes ending on a hit, lanes ending
+      // on an empty stack and lanes that merely pop all run the same short sequence instead of
+      // three serialised divergent copies.
+      if (ray_active && !paused) {
         bool done = hit;
         if (!hit && (G.y & 0xff000000u) == 0u) {
           while (true) {
@@ -673,9 +705,9 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
           if (la_valid) start_queued();
         }
       }
-      const uint32_t act = __ballot_sync(0xffffffffu, ray_active);
-      if (act == 0u) break;
-      if ((uint32_t)__popc(act) < refill_below) {
+      const uint32_t act2 = __ballot_sync(0xffffffffu, ray_active);
+      if (act2 == 0u) break;
+      if ((uint32_t)__popc(act2) < refill_below) {
         // leave only if some idle lane can actually take a new ray
         const bool can = !ray_active && ((have_item && pass < pass_end) || !exhausted);  // (a queued ray would already have started)
         if (__any_sync(0xffffffffu, can)) break;

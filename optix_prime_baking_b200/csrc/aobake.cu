@@ -38,28 +38,47 @@ struct NcclApi {
   int (*GetUniqueId)(NcclId*) = nullptr;
   int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
+  int (*CommAbort)(void*) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   std::string error;
+  template <typename F>
+  bool sym(F& f, const char* name) {
+    f = reinterpret_cast<F>(dlsym(handle, name));
+    if (!f) error = std::string("libnccl lacks the symbol ") + name;
+    return f != nullptr;
+  }
   bool load() {
     if (handle) return true;
-    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    // AOBAKE_NCCL_LIB names the library to bind instead of the default sonames (deployment override;
+    // the tests use it to force a load failure)
+    const char* env = getenv("AOBAKE_NCCL_LIB");
+    const char* names[] = {env && *env ? env : "libnccl.so.2", env && *env ? env : "libnccl.so"};
+    std::string tried;
     for (const char* n : names) {
       handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
       if (handle) break;
+      const char* e = dlerror();   // dlerror() clears the error state: read it exactly once per failure
+      tried = std::string("dlopen(") + n + "): " + (e ? e : "not found");
     }
-    if (!handle) { error = std::string("dlopen(libnccl.so.2): ") + (dlerror() ? dlerror() : "not found"); return false; }
-    GetUniqueId = reinterpret_cast<int (*)(NcclId*)>(dlsym(handle, "ncclGetUniqueId"));
-    CommInitRank = reinterpret_cast<int (*)(void**, int, NcclId, int)>(dlsym(handle, "ncclCommInitRank"));
-    CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(handle, "ncclCommDestroy"));
-    AllReduce = reinterpret_cast<int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)>(dlsym(handle, "ncclAllReduce"));
-    GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(handle, "ncclGetErrorString"));
-    if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce || !GetErrorString) { error = "libnccl lacks an expected symbol"; handle = nullptr; return false; }
+    if (!handle) { error = tried; return false; }
+    if (!sym(GetUniqueId, "ncclGetUniqueId") || !sym(CommInitRank, "ncclCommInitRank") || !sym(CommDestroy, "ncclCommDestroy") ||
+        !sym(CommAbort, "ncclCommAbort") || !sym(AllReduce, "ncclAllReduce") || !sym(AllGather, "ncclAllGather") ||
+        !sym(Broadcast, "ncclBroadcast") || !sym(GroupStart, "ncclGroupStart") || !sym(GroupEnd, "ncclGroupEnd") ||
+        !sym(GetErrorString, "ncclGetErrorString")) {
+      dlclose(handle);
+      handle = nullptr;
+      return false;
+    }
     return true;
   }
 };
 NcclApi g_nccl;
-constexpr int kNcclFloat = 7, kNcclSum = 0;   // ncclFloat32, ncclSum
+constexpr int kNcclFloat = 7, kNcclInt32 = 2, kNcclUint8 = 1, kNcclSum = 0, kNcclMax = 2;   // ncclFloat32, ncclInt32, ncclUint8; ncclSum, ncclMax
 
 template <typename T>
 struct DBuf {
@@ -171,12 +190,15 @@ struct AoBake {
   DBuf<uint32_t> d_deferred_count;
   bool have_ao = false;
   bool have_infos = false;           // sample_infos (tri_idx, bary, dA) are resident — needed by the vertex maps
+  bool unit_normals = true;          // every resident shading normal is unit length (the fp16 node test relies on it)
+  bool samples_sharded = false;      // only this rank's super-blocks of pos/nrm/fnrm are resident (set_samples_distributed)
 
   AoTimings timings{};
 
   // native multi-GPU exchange
   void* nccl_comm = nullptr;
   int comm_rank = 0, comm_size = 1;
+  DBuf<int> d_comm_status;           // one int: the status the ranks agree on before a collective
 
   int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -198,6 +220,49 @@ struct AoBake {
 #define CKL() CK(cudaGetLastError())
 
 namespace {
+
+constexpr uint32_t kDefaultBlockSamples = 65536;   // super-block of the interleaved multi-GPU partition
+constexpr uint32_t kTriBatchFlat = 6, kTriBatchTwoLevel = 6;   // default AoBakeParams::tri_batch (sweep: profiles/r2/sweep_tri_batch.log)
+
+// Makes a local status collective: every rank of the communicator calls this once at the same point
+// with its own status; all of them return non-zero if any rank failed, so that no rank enters the
+// following collective alone (a rank blocked in ncclAllReduce would otherwise hang the job).
+int comm_agree(AoBake* ctx, int rc) {
+  if (ctx->comm_size <= 1 || !ctx->nccl_comm) return rc;
+  cudaStream_t st = ctx->stream;
+  int mine = rc, agreed = rc;
+  bool ok = cudaMemcpyAsync(ctx->d_comm_status.p, &mine, sizeof(int), cudaMemcpyHostToDevice, st) == cudaSuccess;
+  ok = ok && g_nccl.AllReduce(ctx->d_comm_status.p, ctx->d_comm_status.p, 1, kNcclInt32, kNcclMax, ctx->nccl_comm, st) == 0;
+  ok = ok && cudaMemcpyAsync(&agreed, ctx->d_comm_status.p, sizeof(int), cudaMemcpyDeviceToHost, st) == cudaSuccess;
+  ok = ok && cudaStreamSynchronize(st) == cudaSuccess;
+  if (rc) return rc;   // keep the local error text
+  if (!ok) return ctx->fail(AOBAKE_ERR_COMM, "status exchange between the ranks failed");
+  if (agreed) return ctx->fail(AOBAKE_ERR_COMM, "another rank failed with status %d before the collective", agreed);
+  return AOBAKE_OK;
+}
+
+// Host -> device copy of `bytes` bytes.  shard = true (multi-GPU set_scene): every rank holds the same
+// host array, so rank r copies only slice r over its PCIe link and one in-place ncclAllGather over
+// NVLink completes the array on every rank; `dst` must have room for padded_bytes(bytes, nranks).
+size_t shard_chunk(size_t bytes, int nranks) {
+  const size_t c = (bytes + (size_t)nranks - 1) / (size_t)nranks;
+  return (c + 255) & ~(size_t)255;
+}
+size_t padded_bytes(size_t bytes, int nranks) { return nranks > 1 ? shard_chunk(bytes, nranks) * (size_t)nranks : bytes; }
+int upload_bytes(AoBake* ctx, void* dst, const void* src, size_t bytes, bool shard) {
+  if (!bytes) return AOBAKE_OK;
+  cudaStream_t st = ctx->stream;
+  if (!shard || ctx->comm_size <= 1) {
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+    return AOBAKE_OK;
+  }
+  const size_t chunk = shard_chunk(bytes, ctx->comm_size);
+  const size_t b = std::min(bytes, chunk * (size_t)ctx->comm_rank), e = std::min(bytes, b + chunk);
+  if (e > b) CK(cudaMemcpyAsync((char*)dst + b, (const char*)src + b, e - b, cudaMemcpyHostToDevice, st));
+  const int nrc = g_nccl.AllGather((char*)dst + chunk * (size_t)ctx->comm_rank, dst, chunk, kNcclUint8, ctx->nccl_comm, st);
+  if (nrc != 0) return ctx->fail(AOBAKE_ERR_COMM, "ncclAllGather: %s", g_nccl.GetErrorString(nrc));
+  return AOBAKE_OK;
+}
 
 struct Segment {
   uint32_t root = 0;
@@ -280,28 +345,33 @@ int build_segment(AoBake* ctx, const F4* d_plo, const F4* d_phi, uint32_t n, uin
   return AOBAKE_OK;
 }
 
-int upload_mesh(AoBake* ctx, const AoMesh& m, DeviceMesh& dm, bool want_normals) {
+// Device arrays of one mesh: alloc_mesh sizes them (padded for the sharded upload), copy_mesh fills them.
+int alloc_mesh(AoBake* ctx, const AoMesh& m, DeviceMesh& dm, bool want_normals, bool shard) {
   dm.nV = m.num_vertices;
   dm.nT = m.num_triangles;
   if (m.num_vertices > 0xfffffff0ull || m.num_triangles > 0x7ffffff0ull)
     return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "mesh too large for 32-bit indices");
   if ((m.num_vertices && !m.vertices) || (m.num_triangles && !m.tri_vertex_indices))
     return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "mesh has null vertex or index pointer");
+  const int nr = shard ? ctx->comm_size : 1;
+  CK(dm.verts.alloc(padded_bytes(12 * dm.nV, nr) / sizeof(float)));
+  CK(dm.tris.alloc(padded_bytes(12 * dm.nT, nr) / sizeof(uint32_t)));
+  if (want_normals && m.normals) CK(dm.normals.alloc(padded_bytes(12 * dm.nV, nr) / sizeof(float)));
+  return AOBAKE_OK;
+}
+int copy_mesh(AoBake* ctx, const AoMesh& m, DeviceMesh& dm, bool shard) {
   const uint32_t vs = m.vertex_stride_bytes ? m.vertex_stride_bytes : 12u;
   const uint32_t ns = m.normal_stride_bytes ? m.normal_stride_bytes : 12u;
-  CK(dm.verts.alloc(3 * dm.nV));
-  CK(dm.tris.alloc(3 * dm.nT));
-  auto copy_strided = [&](const float* src, uint32_t stride, float* dst) -> cudaError_t {
-    if (dm.nV == 0) return cudaSuccess;
-    if (stride == 12) return cudaMemcpyAsync(dst, src, 12 * dm.nV, cudaMemcpyHostToDevice, ctx->stream);
-    return cudaMemcpy2DAsync(dst, 12, src, stride, 12, dm.nV, cudaMemcpyHostToDevice, ctx->stream);
+  int rc;
+  auto copy_strided = [&](const float* src, uint32_t stride, float* dst) -> int {
+    if (dm.nV == 0) return AOBAKE_OK;
+    if (stride == 12) return upload_bytes(ctx, dst, src, 12 * dm.nV, shard);
+    CK(cudaMemcpy2DAsync(dst, 12, src, stride, 12, dm.nV, cudaMemcpyHostToDevice, ctx->stream));   // strided arrays: every rank copies all of it
+    return AOBAKE_OK;
   };
-  CK(copy_strided(m.vertices, vs, dm.verts.p));
-  if (want_normals && m.normals) {
-    CK(dm.normals.alloc(3 * dm.nV));
-    CK(copy_strided(m.normals, ns, dm.normals.p));
-  }
-  if (dm.nT) CK(cudaMemcpyAsync(dm.tris.p, m.tri_vertex_indices, 12 * dm.nT, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = copy_strided(m.vertices, vs, dm.verts.p))) return rc;
+  if (dm.normals.p && (rc = copy_strided(m.normals, ns, dm.normals.p))) return rc;
+  if ((rc = upload_bytes(ctx, dm.tris.p, m.tri_vertex_indices, 12 * dm.nT, shard))) return rc;
   return AOBAKE_OK;
 }
 
@@ -357,6 +427,8 @@ int alloc_samples(AoBake* ctx, uint64_t n) {
   ctx->num_samples = n;
   ctx->have_ao = false;
   ctx->have_infos = false;
+  ctx->unit_normals = true;
+  ctx->samples_sharded = false;
   const uint64_t m = std::max<uint64_t>(n, 1);
   CK(ctx->d_pos.alloc(3 * m)); CK(ctx->d_nrm.alloc(3 * m)); CK(ctx->d_fnrm.alloc(3 * m)); CK(ctx->d_info.alloc(m));
   CK(ctx->d_ao.alloc(m)); CK(ctx->d_hits.alloc(m));
@@ -402,6 +474,7 @@ int aobake_default_params(AoBakeParams* p) {
   p->leaf_tris = 0;
   p->node_test = 0;
   p->deferred_capacity = 0;
+  p->tri_batch = 0;
   return AOBAKE_OK;
 }
 
@@ -479,8 +552,10 @@ int aobake_synchronize(AoBake* ctx) {
   return AOBAKE_OK;
 }
 
-int aobake_set_scene(AoBake* ctx, const AoScene* scene, const AoScene* blockers) {
+static int set_scene_impl(AoBake* ctx, const AoScene* scene, const AoScene* blockers, bool shard) {
   if (!ctx || !scene) return AOBAKE_ERR_INVALID_ARGUMENT;
+  if (shard && ctx->comm_size > 1 && !ctx->nccl_comm) return ctx->fail(AOBAKE_ERR_STATE, "aobake_comm_init has not been called");
+  shard = shard && ctx->comm_size > 1;
   ScopedTimer tm(ctx);
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
@@ -499,11 +574,17 @@ int aobake_set_scene(AoBake* ctx, const AoScene* scene, const AoScene* blockers)
   // ---- upload ----
   CK(cudaEventRecord(ctx->ev0, st));
   ctx->meshes.resize(scene->num_meshes);
-  for (uint64_t m = 0; m < scene->num_meshes; m++)
-    if ((rc = upload_mesh(ctx, scene->meshes[m], ctx->meshes[m], true))) return rc;
   std::vector<DeviceMesh> bmeshes(blockers ? blockers->num_meshes : 0);
+  rc = AOBAKE_OK;
+  for (uint64_t m = 0; m < scene->num_meshes && !rc; m++) rc = alloc_mesh(ctx, scene->meshes[m], ctx->meshes[m], true, shard);
+  for (size_t m = 0; m < bmeshes.size() && !rc; m++) rc = alloc_mesh(ctx, blockers->meshes[m], bmeshes[m], false, shard);
+  // sharded upload: no rank starts the all-gathers unless every rank could allocate
+  if (shard) rc = comm_agree(ctx, rc);
+  if (rc) return rc;
+  for (uint64_t m = 0; m < scene->num_meshes; m++)
+    if ((rc = copy_mesh(ctx, scene->meshes[m], ctx->meshes[m], shard))) return rc;
   for (size_t m = 0; m < bmeshes.size(); m++)
-    if ((rc = upload_mesh(ctx, blockers->meshes[m], bmeshes[m], false))) return rc;
+    if ((rc = copy_mesh(ctx, blockers->meshes[m], bmeshes[m], shard))) return rc;
   std::vector<HostInstance> binsts;
   auto add_insts = [&](const AoScene* s, std::vector<HostInstance>& dst) {
     for (uint64_t i = 0; i < s->num_instances; i++) {
@@ -753,6 +834,12 @@ int aobake_set_scene(AoBake* ctx, const AoScene* scene, const AoScene* blockers)
   return AOBAKE_OK;
 }
 
+int aobake_set_scene(AoBake* ctx, const AoScene* scene, const AoScene* blockers) { return set_scene_impl(ctx, scene, blockers, false); }
+
+int aobake_set_scene_distributed(AoBake* ctx, const AoScene* scene, const AoScene* blockers) {
+  return set_scene_impl(ctx, scene, blockers, true);
+}
+
 int aobake_distribute_samples(AoBake* ctx, size_t min_per_tri, size_t requested, size_t* per_instance, size_t* total) {
   if (!ctx || !per_instance) return AOBAKE_ERR_INVALID_ARGUMENT;
   if (!ctx->have_scene) return ctx->fail(AOBAKE_ERR_STATE, "distribute_samples before set_scene");
@@ -862,13 +949,14 @@ int aobake_sample_instances(AoBake* ctx, const size_t* per_instance, size_t min_
   return AOBAKE_OK;
 }
 
-int aobake_set_samples(AoBake* ctx, const AoSamples* s, const size_t* per_instance) {
+static int set_samples_impl(AoBake* ctx, const AoSamples* s, const size_t* per_instance, bool shard) {
   if (!ctx || !s) return AOBAKE_ERR_INVALID_ARGUMENT;
   ScopedTimer tm(ctx);
   CK(cudaSetDevice(ctx->device));
   const uint64_t n = s->num_samples;
   if (n && (!s->sample_positions || !s->sample_normals || !s->sample_face_normals))
     return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "null sample arrays");
+  shard = shard && ctx->comm_size > 1;
   int rc;
   if ((rc = alloc_samples(ctx, n))) return rc;
   ctx->per_instance.clear();
@@ -880,16 +968,38 @@ int aobake_set_samples(AoBake* ctx, const AoSamples* s, const size_t* per_instan
   }
   if (n) {
     cudaStream_t st = ctx->stream;
-    CK(cudaMemcpyAsync(ctx->d_pos.p, s->sample_positions, 12 * n, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->d_nrm.p, s->sample_normals, 12 * n, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->d_fnrm.p, s->sample_face_normals, 12 * n, cudaMemcpyHostToDevice, st));
+    DBuf<uint32_t> d_flag;
+    CK(d_flag.alloc(1));
+    CK(cudaMemsetAsync(d_flag.p, 0, sizeof(uint32_t), st));
+    // sharded: only the super-blocks this rank traces (aobake_compute_ao_distributed) cross its PCIe link
+    const uint64_t bs = kDefaultBlockSamples;
+    const uint64_t step = shard ? bs * (uint64_t)ctx->comm_size : n;
+    for (uint64_t b = shard ? bs * (uint64_t)ctx->comm_rank : 0; b < n; b += step) {
+      const uint64_t e = shard ? std::min(n, b + bs) : n;
+      CK(cudaMemcpyAsync(ctx->d_pos.p + 3 * b, s->sample_positions + 3 * b, 12 * (e - b), cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(ctx->d_nrm.p + 3 * b, s->sample_normals + 3 * b, 12 * (e - b), cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(ctx->d_fnrm.p + 3 * b, s->sample_face_normals + 3 * b, 12 * (e - b), cudaMemcpyHostToDevice, st));
+      k_check_unit_normals<<<grid_for(e - b, 256), 256, 0, st>>>(ctx->d_nrm.p, b, e, d_flag.p);
+    }
+    CKL();
     if (s->sample_infos) {
       CK(cudaMemcpyAsync(ctx->d_info.p, s->sample_infos, sizeof(AoSampleInfo) * n, cudaMemcpyHostToDevice, st));
       ctx->have_infos = true;
     }
+    uint32_t flag = 0;
+    CK(cudaMemcpyAsync(&flag, d_flag.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    ctx->unit_normals = flag == 0;
+    ctx->samples_sharded = shard;
   }
   return AOBAKE_OK;
+}
+
+int aobake_set_samples(AoBake* ctx, const AoSamples* s, const size_t* per_instance) { return set_samples_impl(ctx, s, per_instance, false); }
+
+int aobake_set_samples_distributed(AoBake* ctx, const AoSamples* s, const size_t* per_instance) {
+  if (ctx && ctx->comm_size > 1 && !ctx->nccl_comm) return ctx->fail(AOBAKE_ERR_STATE, "aobake_comm_init has not been called");
+  return set_samples_impl(ctx, s, per_instance, true);
 }
 
 size_t aobake_num_samples(const AoBake* ctx) { return ctx ? ctx->num_samples : 0; }
@@ -900,6 +1010,9 @@ static int compute_ao_impl(AoBake* ctx, size_t begin, size_t end, int rays_per_s
   if (!ctx->have_scene) return ctx->fail(AOBAKE_ERR_STATE, "compute_ao before set_scene");
   if (begin > end || end > ctx->num_samples) return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "sample range [%zu,%zu) outside [0,%llu)", begin, end, (unsigned long long)ctx->num_samples);
   if (rays_per_sample < 1) return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "rays_per_sample must be >= 1");
+  if (ctx->samples_sharded && !(num_parts == (uint32_t)ctx->comm_size && part == (uint32_t)ctx->comm_rank && begin == 0 && end == ctx->num_samples &&
+                                (block_samples == 0 || block_samples == kDefaultBlockSamples)))
+    return ctx->fail(AOBAKE_ERR_STATE, "only this rank's super-blocks are resident (aobake_set_samples_distributed): use aobake_compute_ao_distributed");
   ScopedTimer tm(ctx);
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
@@ -912,7 +1025,7 @@ static int compute_ao_impl(AoBake* ctx, size_t begin, size_t end, int rays_per_s
   uint64_t n_local_blocks = n_global_blocks, owned_samples = n;
   if (num_parts > 1) {
     if (part >= num_parts) return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "part %u of %u", part, num_parts);
-    if (block_samples == 0) block_samples = 65536;
+    if (block_samples == 0) block_samples = kDefaultBlockSamples;
     if (block_samples % 32) return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "block_samples must be a multiple of 32");
     sb_blocks = block_samples / 32;
     const uint64_t n_sb = (n_global_blocks + sb_blocks - 1) / sb_blocks;
@@ -954,20 +1067,19 @@ static int compute_ao_impl(AoBake* ctx, size_t begin, size_t end, int rays_per_s
     if (n_chunks > 1) CK(cudaMemsetAsync(ctx->d_hits.p + begin, 0, n * sizeof(uint32_t), st));
     const uint64_t warps = n_blocks * n_chunks;
     const unsigned grid = grid_for(warps * 32, 256);
-    if (stats)
-      k_ao_simple<true><<<grid, 256, 0, st>>>(bvh, S, begin, end, q, offset, maxdist, n_chunks, ctx->d_hits.p + begin, ctx->d_stats.p);
-    else
-      k_ao_simple<false><<<grid, 256, 0, st>>>(bvh, S, begin, end, q, offset, maxdist, n_chunks, ctx->d_hits.p + begin, ctx->d_stats.p);
+    const bool h2 = AOB_H2 != 0 && ctx->params.node_test != 1;   // per ray: trace_any_hit checks direction range and length itself
+    auto kern = h2 ? (stats ? k_ao_simple<true, true> : k_ao_simple<false, true>) : (stats ? k_ao_simple<true, false> : k_ao_simple<false, false>);
+    kern<<<grid, 256, 0, st>>>(bvh, S, begin, end, q, offset, maxdist, n_chunks, ctx->d_hits.p + begin, ctx->d_stats.p);
     CKL();
     launches++;
   } else {
     // persistent variant: one resident wave of CTAs (a multiple of the SM count), dynamic work fetch
     if (n > 0xfffffff0ull) return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "more than 2^32 samples in one range");
-    using KernelT = void (*)(BvhView, SampleView, uint64_t, uint32_t, int, float, float, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t,
+    using KernelT = void (*)(BvhView, SampleView, uint64_t, uint32_t, int, float, float, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t,
                              uint32_t, uint32_t*, unsigned long long*, unsigned long long*, DeferredRays);
     // node test: packed fp16 (two planes per instruction) for flattened scenes, unless asked otherwise
     // or a previous attempt overflowed the deferred-ray list; fp32 under a TLAS (measured faster there)
-    use_h2 = AOB_H2 != 0 && !force_fp32 && ctx->params.node_test != 1 && !ctx->two_level;
+    use_h2 = AOB_H2 != 0 && !force_fp32 && ctx->params.node_test != 1 && !ctx->two_level && ctx->unit_normals;
     // the far clamp of the fp32 node test is only needed when maxdist can actually cull inside the scene
     const bool clamp = !(maxdist > 1.01f * ctx->scene_diag + fabsf(offset));
     KernelT kern;
@@ -1001,7 +1113,9 @@ static int compute_ao_impl(AoBake* ctx, size_t begin, size_t end, int rays_per_s
       deferred.list = ctx->d_deferred.p; deferred.count = ctx->d_deferred_count.p; deferred.capacity = (uint32_t)ctx->d_deferred.n;
     }
     const uint32_t refill = ctx->params.refill_below > 0 ? (uint32_t)ctx->params.refill_below : 28u;
-    kern<<<grid, kAoBlock, 0, st>>>(bvh, S, (uint64_t)begin, (uint32_t)n, q, offset, maxdist, n_chunks, refill, part, num_parts, sb_blocks,
+    // lanes that must hold leaf hits before the warp runs its triangle block (1 = test at once)
+    const uint32_t tri_batch = ctx->params.tri_batch > 0 ? (uint32_t)std::min(ctx->params.tri_batch, 32) : (ctx->two_level ? kTriBatchTwoLevel : kTriBatchFlat);
+    kern<<<grid, kAoBlock, 0, st>>>(bvh, S, (uint64_t)begin, (uint32_t)n, q, offset, maxdist, n_chunks, refill, tri_batch, part, num_parts, sb_blocks,
                                     (uint32_t)n_local_blocks, ctx->d_hits.p + begin, ctx->d_counter.p, ctx->d_stats.p, deferred);
     CKL();
     launches++;
@@ -1067,6 +1181,8 @@ int aobake_comm_init(AoBake* ctx, int rank, int nranks, const void* id128) {
   if (rc != 0) return ctx->fail(AOBAKE_ERR_COMM, "ncclCommInitRank: %s", g_nccl.GetErrorString(rc));
   ctx->comm_rank = rank;
   ctx->comm_size = nranks;
+  g_alloc_stream = ctx->stream;
+  CK(ctx->d_comm_status.alloc(1));
   return AOBAKE_OK;
 }
 
@@ -1088,7 +1204,7 @@ int aobake_compute_ao_distributed(AoBake* ctx, int rays_per_sample, float offset
   if (ctx->comm_size > 1 && !ctx->nccl_comm) return ctx->fail(AOBAKE_ERR_STATE, "aobake_comm_init has not been called");
   int rc = compute_ao_impl(ctx, 0, ctx->num_samples, rays_per_sample, offset, maxdist, nullptr, (uint32_t)ctx->comm_rank,
                            (uint32_t)ctx->comm_size, 0);
-  if (rc) return rc;
+  if ((rc = comm_agree(ctx, rc))) return rc;   // a rank that failed locally must not leave the others in the all-reduce
   cudaStream_t st = ctx->stream;
   if (ctx->comm_size > 1 && ctx->num_samples) {
     // every rank holds exact zeros outside its super-blocks: the sum assembles ao[] bit for bit
@@ -1326,6 +1442,7 @@ static int map_ao_impl(AoBake* ctx, int mode, float weight, float* const* host_v
   }
   DBuf<float> d_sub;
   int rc = mode == AOBAKE_FILTER_LEAST_SQUARES ? ls_filter_batched(ctx, weight, ib, ie, d_sub) : area_filter_batched(ctx, ib, ie, d_sub);
+  if (dist) rc = comm_agree(ctx, rc);   // e.g. a CG breakdown on one rank must not strand the others in the all-reduce
   if (rc) return rc;
   const float* d_all = d_sub.p;   // vertex AO of every instance, global numbering
   DBuf<float> d_full;
@@ -1391,7 +1508,8 @@ int aobake_trace_rays(AoBake* ctx, const float* rays, size_t n, uint8_t* hit) {
   DBuf<uint8_t> d_hit;
   CK(d_rays.alloc(8 * n)); CK(d_hit.alloc(n));
   CK(cudaMemcpyAsync(d_rays.p, rays, 32 * n, cudaMemcpyHostToDevice, st));
-  k_trace_rays<<<grid_for(n, 128), 128, 0, st>>>(bvh_view(ctx), d_rays.p, n, d_hit.p);
+  if (AOB_H2 != 0 && ctx->params.node_test != 1) k_trace_rays<true><<<grid_for(n, 128), 128, 0, st>>>(bvh_view(ctx), d_rays.p, n, d_hit.p);
+  else k_trace_rays<false><<<grid_for(n, 128), 128, 0, st>>>(bvh_view(ctx), d_rays.p, n, d_hit.p);
   CKL();
   CK(cudaMemcpyAsync(hit, d_hit.p, n, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));

@@ -163,7 +163,33 @@ def value_noise(x: np.ndarray, z: np.ndarray, seed: int, octaves: int = 4) -> np
 def heightfield(n: int = 708, seed: int = 1, size: float = 10.0, height: float = 1.5,
                 base_freq: float = 6.0, warp: float = 0.0) -> Mesh:
     """(n x n)-cell terrain: 2*n*n triangles, up = +Y.  warp > 0 makes the grid spacing (and so
-    the triangle areas) non-uniform (config 3, SURVEY §7 'area distribution quirk')."""
+    the triangle areas) non-uniform (config 3, SURVEY §7 'area distribution quirk').
+    Large grids (config 3: 27 s of numpy) are cached as .npy files in a scratch directory, so that the
+    ranks of one job and back-to-back runs on one box generate them once."""
+    if n >= 2000:
+        import os
+        import tempfile
+        d = os.environ.get("AOBAKE_SCENE_CACHE", os.path.join(tempfile.gettempdir(), "aobake_scene_cache"))
+        stem = os.path.join(d, f"hf_v1_{n}_{seed}_{size}_{height}_{base_freq}_{warp}")
+        try:
+            return Mesh(np.load(stem + "_v.npy"), np.load(stem + "_t.npy"), np.load(stem + "_n.npy"))
+        except (OSError, ValueError):
+            pass
+        m = _heightfield(n, seed, size, height, base_freq, warp)
+        try:
+            os.makedirs(d, exist_ok=True)
+            for suffix, arr in (("_v.npy", m.vertices), ("_t.npy", m.tris), ("_n.npy", m.normals)):
+                tmp = f"{stem}{suffix}.{os.getpid()}.tmp"
+                with open(tmp, "wb") as f:
+                    np.save(f, arr)
+                os.replace(tmp, stem + suffix)   # atomic: a concurrent reader sees the old state or the whole file
+        except OSError:
+            pass
+        return m
+    return _heightfield(n, seed, size, height, base_freq, warp)
+
+
+def _heightfield(n: int, seed: int, size: float, height: float, base_freq: float, warp: float) -> Mesh:
     u = np.arange(n + 1, dtype=np.float64) / n
     if warp > 0.0:
         u = u + warp * np.sin(2 * np.pi * u) / (2 * np.pi)

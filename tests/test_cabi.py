@@ -4,6 +4,7 @@ import ctypes
 import os
 import re
 import subprocess
+import sys
 
 import pytest
 
@@ -116,3 +117,21 @@ def test_ctypes_mirrors_match_the_c_compiler(tmp_path):
             C.sizeof(ct.AoSamples), C.sizeof(api.AoBakeParams), api.AoBakeParams.refill_below.offset, C.sizeof(api.AoTimings),
             api.AoTimings.rays_traced.offset, C.sizeof(api.AoStats)]
     assert got == want
+
+
+def test_missing_nccl_is_a_status_not_a_crash(lib_path):
+    """ADVICE r1: NcclApi::load() once built its message from two dlerror() calls and dereferenced NULL.
+    With the NCCL library unresolvable, aobake_comm_unique_id must return AOBAKE_ERR_COMM and a message
+    (needs no GPU: binding NCCL is a dlopen)."""
+    code = ("import ctypes, sys\n"
+            f"L = ctypes.CDLL({lib_path!r})\n"
+            "L.aobake_last_error.restype = ctypes.c_char_p\n"
+            "L.aobake_last_error.argtypes = [ctypes.c_void_p]\n"
+            "buf = ctypes.create_string_buffer(128)\n"
+            "rc = L.aobake_comm_unique_id(buf)\n"
+            "msg = L.aobake_last_error(None).decode()\n"
+            "print(rc, msg)\n"
+            "sys.exit(0 if rc == 7 and 'dlopen' in msg else 1)\n")
+    env = dict(os.environ, AOBAKE_NCCL_LIB="/nonexistent/libnccl-missing.so")
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=60)
+    assert res.returncode == 0, res.stdout + res.stderr

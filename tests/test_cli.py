@@ -52,6 +52,18 @@ def test_cli_builds_and_rejects_bad_flags(tmp_path):
     assert subprocess.run([exe, "-f", "/nonexistent.obj"], capture_output=True).returncode == 1
 
 
+def test_cli_rejects_malformed_obj_files(tmp_path):
+    """face indices were used before they were validated.  A zero / out-of-range vertex index,
+    or a normal index past the vn count, must be `could not load` (exit 1), not a heap overrun."""
+    exe = build_cli(tmp_path)
+    head = "v 0 0 0\nv 1 0 0\nv 0 1 0\nvn 0 0 1\n"
+    for k, face in enumerate(["f 0//1 1//1 2//1", "f 1//1 2//1 9//1", "f 1//1 2//1 3//7", "f 1//1 2//1 -9//1", "f 1//-5 2//1 3//1"]):
+        path = tmp_path / f"bad{k}.obj"
+        path.write_text(head + face + "\n")
+        res = subprocess.run([exe, "-f", str(path), "--no_viewer"], capture_output=True, text=True)
+        assert res.returncode == 1, (face, res.returncode, res.stderr)
+
+
 @pytest.mark.gpu
 def test_cli_bake_matches_python_api(tmp_path):
     from optix_prime_baking_b200 import api

@@ -22,6 +22,8 @@
 #include <fstream>
 #include <sstream>
 #include <string>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -74,30 +76,30 @@ bool load_obj(const std::string& path, HostMesh& m, bool flip) {
       }
     }
   }
-  const size_t nv = m.v.size() / 3;
-  m.n.assign(m.v.size(), 0.0f);
-  std::vector<int> assigned(nv, -1);
-  bool ok_normals = !vn.empty();
-  for (size_t i = 0; i < corner_v.size() && ok_normals; i++) {
-    const int v = corner_v[i], n = corner_n[i];
-    if (n < 0) { ok_normals = false; break; }
-    if (assigned[v] >= 0 && assigned[v] != n) {
-      // same position with different normals (a crease): average them
-    }
-    assigned[v] = n;
-    for (int k = 0; k < 3; k++) m.n[3 * v + k] += (flip ? -1.0f : 1.0f) * vn[3 * n + k];
+  const size_t nv = m.v.size() / 3, nn = vn.size() / 3;
+  // validate every index BEFORE it is used (a face may reference vertices or normals declared later in the
+  // file, so this cannot be done while parsing): a malformed OBJ is "could not load", not a heap overrun
+  for (int c : corner_v)
+    if (c < 0 || (size_t)c >= nv) return false;
+  bool ok_normals = nn > 0;
+  for (int n : corner_n) {
+    if (n < 0) { ok_normals = false; continue; }   // a corner without a normal: fall back to face normals
+    if ((size_t)n >= nn) return false;
   }
-  if (!ok_normals) m.n.clear();
-  else
+  if (ok_normals) {
+    // per-vertex normal = normalised sum of the normals its corners reference (creases are averaged)
+    m.n.assign(m.v.size(), 0.0f);
+    for (size_t i = 0; i < corner_v.size(); i++)
+      for (int k = 0; k < 3; k++) m.n[3 * (size_t)corner_v[i] + k] += (flip ? -1.0f : 1.0f) * vn[3 * (size_t)corner_n[i] + k];
     for (size_t v = 0; v < nv; v++) {
       float* p = &m.n[3 * v];
       const float l = std::sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
       if (l > 0) { p[0] /= l; p[1] /= l; p[2] /= l; }
     }
-  for (int c : corner_v) {
-    if (c < 0 || (size_t)c >= nv) return false;
-    m.t.push_back((unsigned)c);
+  } else {
+    m.n.clear();
   }
+  for (int c : corner_v) m.t.push_back((unsigned)c);
   return !m.v.empty() && !m.t.empty();
 }
 
@@ -254,6 +256,14 @@ int main(int argc, char** argv) {
     char id[AOBAKE_COMM_ID_BYTES];
     if (aobake_comm_unique_id(id) != AOBAKE_OK) { fprintf(stderr, "NCCL: %s\n", aobake_last_error(nullptr)); aobake_destroy(ctx); return 1; }
     std::vector<int> rcs(cfg.gpus, AOBAKE_OK);
+    // Two phases, so that one failing rank cannot strand the others inside ncclCommInitRank: every helper
+    // first creates its context, uploads the scene and samples; only if ALL of them succeeded does anyone
+    // enter the communicator set-up.  (Inside the library a rank that fails later makes the collective
+    // entry points return AOBAKE_ERR_COMM on every rank instead of blocking.)
+    std::mutex mu;
+    std::condition_variable cv;
+    int prepared = 0;
+    bool go = false, abort_all = false;
     auto helper = [&](int rank) {
       AoBakeParams p;
       aobake_default_params(&p);
@@ -262,18 +272,40 @@ int main(int argc, char** argv) {
       int rc = aobake_create(&p, &c);
       if (rc == AOBAKE_OK) rc = aobake_set_scene(c, &scene, cfg.ground ? &blockers : nullptr);
       if (rc == AOBAKE_OK) rc = aobake_sample_instances(c, per.data(), (size_t)cfg.samples_per_face, nullptr);
-      if (rc == AOBAKE_OK) rc = aobake_comm_init(c, rank, cfg.gpus, id);
-      if (rc == AOBAKE_OK) rc = aobake_compute_ao_distributed(c, cfg.rays, scene_offset, scene_maxdist, nullptr);
       if (rc != AOBAKE_OK) fprintf(stderr, "rank %d: %s\n", rank, c ? aobake_last_error(c) : aobake_last_error(nullptr));
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        prepared++;
+        if (rc != AOBAKE_OK) abort_all = true;
+        cv.notify_all();
+        cv.wait(lk, [&] { return go; });
+      }
+      if (!abort_all) {
+        rc = aobake_comm_init(c, rank, cfg.gpus, id);
+        if (rc == AOBAKE_OK) rc = aobake_compute_ao_distributed(c, cfg.rays, scene_offset, scene_maxdist, nullptr);
+        if (rc != AOBAKE_OK) fprintf(stderr, "rank %d: %s\n", rank, aobake_last_error(c));
+      }
       rcs[rank] = rc;
       if (c) aobake_destroy(c);
     };
     std::vector<std::thread> th;
     for (int r = 1; r < cfg.gpus; r++) th.emplace_back(helper, r);
-    ck(aobake_comm_init(ctx, 0, cfg.gpus, id), "comm_init");
-    ck(aobake_compute_ao_distributed(ctx, cfg.rays, scene_offset, scene_maxdist, nullptr), "compute_ao_distributed");
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      cv.wait(lk, [&] { return prepared == cfg.gpus - 1; });
+      go = true;
+      cv.notify_all();
+    }
+    int rc0 = AOBAKE_OK;
+    if (!abort_all) {
+      rc0 = aobake_comm_init(ctx, 0, cfg.gpus, id);
+      if (rc0 == AOBAKE_OK) rc0 = aobake_compute_ao_distributed(ctx, cfg.rays, scene_offset, scene_maxdist, nullptr);
+      if (rc0 != AOBAKE_OK) fprintf(stderr, "rank 0: %s\n", aobake_last_error(ctx));
+    }
     for (auto& x : th) x.join();
-    for (int r = 1; r < cfg.gpus; r++) if (rcs[r] != AOBAKE_OK) { aobake_destroy(ctx); return 1; }
+    bool failed = abort_all || rc0 != AOBAKE_OK;
+    for (int r = 1; r < cfg.gpus; r++) failed = failed || rcs[r] != AOBAKE_OK;
+    if (failed) { fprintf(stderr, "multi-GPU bake failed\n"); aobake_destroy(ctx); return 1; }
   } else {
     ck(aobake_compute_ao(ctx, cfg.rays, scene_offset, scene_maxdist, nullptr), "compute_ao");
   }
