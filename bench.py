@@ -41,7 +41,7 @@ if ROOT not in sys.path:
 
 from optix_prime_baking_b200 import scenes  # noqa: E402
 
-RAYS = {"c1": 64, "c2": 256, "c3": 1024, "c4": 256}
+RAYS = {"c1": 64, "c2": 256, "c3": 1024, "c4": 256, "c5": 1024}
 BLOCK_SAMPLES = 65536
 PROFILE_ROUND = "r2"
 
@@ -56,6 +56,9 @@ def make_workload(name: str):
     if name == "c3":
         scene, blockers = scenes.config3_bigmesh()
         return scene, blockers, 0, 10_000_000, "20M-tri warped heightfield, 10M area-weighted samples, 1024 rays/sample"
+    if name == "c5":
+        scene, blockers = scenes.config3_bigmesh(with_ground=True)
+        return scene, blockers, 0, 10_000_000, "20M-tri warped heightfield + ground-plane blocker, 10M area-weighted samples, 1024 rays/sample"
     if name == "c4":
         scene, blockers = scenes.config4_instanced()
         return scene, blockers, 3, 0, "1000 instances of a 49.6k-tri mesh (TLAS/BLAS), 3 samples/face, 256 rays/sample"
@@ -388,13 +391,17 @@ def main():
     e2e_s = max_over_ranks(float(np.mean(e2e_times)))
     e2e_value = rays_job / e2e_s / 1e6
     ao_mean = float(ao_host.mean())
+    # the host-buffer path (sharded uploads + all-gather) must reproduce the resident path bit for bit
+    bk.sample_instances(per, min_per, download=False)
+    e2e_same = bool(np.array_equal(bk.compute_ao_distributed(rays, off, maxd).view(np.uint32), ao_host.view(np.uint32)))
+    assert e2e_same, "host-buffer (e2e) AO differs from the resident path"
     h2d = int(max_over_ranks(0.0) + sum_over_ranks(torch, dist, world, h2d_rank))
     d2h = int(sum_over_ranks(torch, dist, world, d2h_rank))
 
     # ------------------------------------------------------------------ bake_s: end-to-end bake (config 5 for c3)
     bake = None
     if not args.no_bake:
-        if args.workload == "c3":
+        if args.workload in ("c3", "c5"):
             bscene, bblockers = scene_pin, pinned_scene(scenes.ground_blockers(scene))
             bmode, bdesc = api.FILTER_LEAST_SQUARES, "BASELINE.json configs[4]: the 20M-tri mesh + ground-plane blocker + least-squares vertex filter (w = 0.1)"
         else:
@@ -475,7 +482,7 @@ def main():
                     "what": "computeAO(scene, blockers, samples) with pinned host buffers on every rank: scene upload (1/N per rank + "
                             "ncclAllGather) + BVH build + upload of the rank's sample super-blocks + trace + all-reduce + download of ao[]; "
                             "bytes are summed over the ranks", "seconds_per_step": e2e_s, "steps": e2e_steps, "breakdown_rank0": e2e_break,
-                    "ao_mean": ao_mean},
+                    "ao_mean": ao_mean, "bit_identical_to_resident_path": e2e_same},
             "bake_s": bake["seconds"] if bake else None,
             "bake": bake,
             "gpu_launches": int(launches_per_step) * args.steps,

@@ -123,7 +123,13 @@ typedef struct AoBakeParams {
                                      aobake_compute_ao repeat the launch with the fp32 kernels — settable so that tests can force it */
   int32_t tri_batch;              /* fused kernel: lanes of a warp that must hold leaf hits before the warp runs its triangle
                                      block (paused lanes take no node steps meanwhile); 1 = test at once, 0 = default */
-  int32_t reserved[3];
+  int32_t no_oversized_split;     /* BVH build: 0 = primitives (or TLAS instances) spanning more than a quarter of the scene (a ground
+                                     plane under a fine mesh) are kept out of the tree and hang off one extra root node; 1 = build
+                                     one tree over everything (A/B switch; both give the same hits) */
+  int32_t ls_energy;              /* least-squares regulariser per interior edge: 0 = (A1 + A2) |grad(T1) - grad(T2)|^2, the 3-D
+                                     gradient jump of Kavan et al. 2011; 1 = (A1 + A2)^2 x (jump of the co-normal
+                                     derivative)^2, the scale-free variant of round 1 (same null space, far better conditioned) */
+  int32_t reserved[1];
 } AoBakeParams;
 
 typedef struct AoTimings {        /* milliseconds, device-timed with CUDA events unless noted */

@@ -163,6 +163,113 @@ __global__ void k_morton(const F4* __restrict__ plo, const F4* __restrict__ phi,
   keys[i] = morton63(plo[i], phi[i], cmin, cinv);
   vals[i] = i;
 }
+// ---- oversized primitives (a ground-plane quad under a fine mesh, a huge instance in a TLAS) ----------
+// A primitive whose box spans a large part of the scene poisons the top of an LBVH: every node that
+// contains it has a scene-sized box, the 8-bit grids of those nodes are hundreds of leaf-sizes coarse, and
+// the children that hold the real geometry are so inflated by the quantisation that every ray visits all of
+// them (config 5: 15.1 node visits per ray instead of 6.9 for the same mesh without its ground plane).
+// Such primitives are kept out of the tree: flagged here, sorted behind everything else (key = ~0), and
+// attached as leaf slots of one extra root node whose only internal child is the root of the tree over the
+// rest — one coarse node on top, precise grids everywhere below.
+__global__ void k_flag_big(const F4* __restrict__ plo, const F4* __restrict__ phi, uint32_t n, const int* __restrict__ f6,
+                           uint8_t* __restrict__ big, uint32_t* __restrict__ count) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float sx = ordered_to_float(f6[3]) - ordered_to_float(f6[0]), sy = ordered_to_float(f6[4]) - ordered_to_float(f6[1]),
+              sz = ordered_to_float(f6[5]) - ordered_to_float(f6[2]);
+  const float ext = fmaxf(sx, fmaxf(sy, sz));
+  const F4 lo = plo[i], hi = phi[i];
+  const float pe = fmaxf(hi.x - lo.x, fmaxf(hi.y - lo.y, hi.z - lo.z));
+  const bool b = pe > 0.25f * ext;
+  big[i] = b ? 1 : 0;
+  if (b) atomicAdd(count, 1u);
+}
+// centroid bounds (b6) and box bounds (f6) of the primitives that are NOT flagged
+__global__ void k_bounds_small(const F4* __restrict__ plo, const F4* __restrict__ phi, const uint8_t* __restrict__ big, uint32_t n, int* b6, int* f6) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  float c[3] = {3.0e38f, 3.0e38f, 3.0e38f}, C[3] = {-3.0e38f, -3.0e38f, -3.0e38f}, l[3] = {3.0e38f, 3.0e38f, 3.0e38f}, h[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+  if (i < n && !big[i]) {
+    const F4 lo = plo[i], hi = phi[i];
+    c[0] = C[0] = 0.5f * (lo.x + hi.x); c[1] = C[1] = 0.5f * (lo.y + hi.y); c[2] = C[2] = 0.5f * (lo.z + hi.z);
+    l[0] = lo.x; l[1] = lo.y; l[2] = lo.z; h[0] = hi.x; h[1] = hi.y; h[2] = hi.z;
+  }
+#pragma unroll
+  for (int k = 0; k < 3; k++)
+    for (int o = 16; o > 0; o >>= 1) {
+      c[k] = fminf(c[k], __shfl_xor_sync(0xffffffffu, c[k], o)); C[k] = fmaxf(C[k], __shfl_xor_sync(0xffffffffu, C[k], o));
+      l[k] = fminf(l[k], __shfl_xor_sync(0xffffffffu, l[k], o)); h[k] = fmaxf(h[k], __shfl_xor_sync(0xffffffffu, h[k], o));
+    }
+  if ((threadIdx.x & 31) == 0 && c[0] < 3.0e38f) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      atomicMin(&b6[k], float_to_ordered(c[k])); atomicMax(&b6[3 + k], float_to_ordered(C[k]));
+      atomicMin(&f6[k], float_to_ordered(l[k])); atomicMax(&f6[3 + k], float_to_ordered(h[k]));
+    }
+  }
+}
+__global__ void k_morton_small(const F4* __restrict__ plo, const F4* __restrict__ phi, const uint8_t* __restrict__ big, uint32_t n,
+                               const int* __restrict__ b6, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const V3 cmin = v3(ordered_to_float(b6[0]), ordered_to_float(b6[1]), ordered_to_float(b6[2]));
+  const V3 cmax = v3(ordered_to_float(b6[3]), ordered_to_float(b6[4]), ordered_to_float(b6[5]));
+  const float ext = fmaxf(cmax.x - cmin.x, fmaxf(cmax.y - cmin.y, cmax.z - cmin.z));
+  const float inv = ext > 0.0f ? 1.0f / ext : 0.0f;
+  keys[i] = big[i] ? ~0ull : morton63(plo[i], phi[i], cmin, v3(inv, inv, inv));   // 63-bit codes: ~0 sorts behind all of them
+  vals[i] = i;
+}
+// The extra root: slot 0 = the tree over the ordinary primitives (node `main_root`, box f6_small), the
+// following slots = the oversized primitives (sorted positions [n_small, n), `per_slot` per slot), which
+// also complete the leaf order.  One thread.
+__global__ void k_super_root(Node8* __restrict__ nodes, uint32_t node_index, uint32_t main_root, const int* __restrict__ f6_all,
+                             const int* __restrict__ f6_small, const F4* __restrict__ plo, const F4* __restrict__ phi,
+                             const uint32_t* __restrict__ sorted_prims, uint32_t n_small, uint32_t n_big, uint32_t per_slot,
+                             uint32_t prim_offset, uint32_t* __restrict__ leaf_prims) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  F4 nlo, nhi;
+  nlo.x = ordered_to_float(f6_all[0]); nlo.y = ordered_to_float(f6_all[1]); nlo.z = ordered_to_float(f6_all[2]); nlo.w = 0.f;
+  nhi.x = ordered_to_float(f6_all[3]); nhi.y = ordered_to_float(f6_all[4]); nhi.z = ordered_to_float(f6_all[5]); nhi.w = 0.f;
+  Node8 nd;
+  nd.px = nlo.x; nd.py = nlo.y; nd.pz = nlo.z;
+  uint32_t ex = quant_exponent(nhi.x - nlo.x), ey = quant_exponent(nhi.y - nlo.y), ez = quant_exponent(nhi.z - nlo.z);
+  {
+    uint32_t em = ex > ey ? ex : ey;   // same rule as collapse_body: steps within 2^kExpSpread of the widest
+    em = em > ez ? em : ez;
+    if (em < 24u) em = 24u;
+    const uint32_t fl = em - (uint32_t)kExpSpread;
+    ex = ex > fl ? ex : fl; ey = ey > fl ? ey : fl; ez = ez > fl ? ez : fl;
+  }
+  nd.ex = (uint8_t)ex; nd.ey = (uint8_t)ey; nd.ez = (uint8_t)ez;
+  nd.child_base = main_root;
+  nd.prim_base = prim_offset + n_small;
+  nd.imask = 1u;
+  for (int k = 0; k < 8; k++) {
+    nd.meta[k] = 0;
+    for (int a = 0; a < 3; a++) { nd.q[a][k][0] = 255; nd.q[a][k][1] = 0; }
+  }
+  nd.meta[0] = (uint8_t)(0x20u | 24u);
+  quantize_axis(nlo.x, ex, ordered_to_float(f6_small[0]), ordered_to_float(f6_small[3]), &nd.q[0][0][0], &nd.q[0][0][1]);
+  quantize_axis(nlo.y, ey, ordered_to_float(f6_small[1]), ordered_to_float(f6_small[4]), &nd.q[1][0][0], &nd.q[1][0][1]);
+  quantize_axis(nlo.z, ez, ordered_to_float(f6_small[2]), ordered_to_float(f6_small[5]), &nd.q[2][0][0], &nd.q[2][0][1]);
+  uint32_t po = 0;
+  for (uint32_t k = 1; k < 8 && po < n_big; k++) {
+    const uint32_t cnt = min(per_slot, n_big - po);
+    F4 lo, hi;
+    lo.x = lo.y = lo.z = 3.0e38f; hi.x = hi.y = hi.z = -3.0e38f;
+    for (uint32_t j = 0; j < cnt; j++) {
+      const uint32_t p = sorted_prims[n_small + po + j];
+      leaf_prims[n_small + po + j] = p;
+      lo.x = fminf(lo.x, plo[p].x); lo.y = fminf(lo.y, plo[p].y); lo.z = fminf(lo.z, plo[p].z);
+      hi.x = fmaxf(hi.x, phi[p].x); hi.y = fmaxf(hi.y, phi[p].y); hi.z = fmaxf(hi.z, phi[p].z);
+    }
+    quantize_axis(nlo.x, ex, lo.x, hi.x, &nd.q[0][k][0], &nd.q[0][k][1]);
+    quantize_axis(nlo.y, ey, lo.y, hi.y, &nd.q[1][k][0], &nd.q[1][k][1]);
+    quantize_axis(nlo.z, ez, lo.z, hi.z, &nd.q[2][k][0], &nd.q[2][k][1]);
+    nd.meta[k] = (uint8_t)((((1u << cnt) - 1u) << 5) | po);
+    po += cnt;
+  }
+  nodes[node_index] = nd;
+}
 __global__ void k_hierarchy(Lbvh L) { lbvh_hierarchy_body(blockIdx.x * blockDim.x + threadIdx.x, L); }
 __global__ void k_refit(Lbvh L) { lbvh_refit_body(blockIdx.x * blockDim.x + threadIdx.x, L); }
 __global__ void k_collapse(CollapseArgs A, uint32_t lb, uint32_t le) {
@@ -770,10 +877,19 @@ __global__ void k_ls_halfedges(const uint32_t* __restrict__ tris, uint64_t nT, u
   keys[i] = (a == b) ? ~0ull : (((uint64_t)min(a, b) << 32) | max(a, b));
   vals[i] = (uint32_t)i;
 }
+// One interior edge (i, j) with opposite vertices p, q (global vertex numbers): s = foot parameter of the
+// opposite vertex along the edge, h = its altitude, c = m1 . m2 (the unit in-plane edge normals pointing at
+// p and q; -1 for a flat pair), W = energy weight.  Energy = W (a1^2 + a2^2 - 2 c a1 a2) with
+// a1 = (x_p - s1 x_j - (1 - s1) x_i) / h1, a2 likewise with q — the squared jump of the 3-D gradient of the
+// piecewise-linear interpolant across the edge times (A1 + A2) (see oracle/ao_oracle.cpp).
 struct LsEdge {
   uint32_t i, j, p, q;
-  double c[4];
+  double s1, h1, s2, h2, c, W;   // W == 0: degenerate edge, contributes nothing
 };
+AOB_D void ls_edge_coeffs(const LsEdge& E, double* al, double* be) {
+  al[0] = -(1.0 - E.s1) / E.h1; al[1] = -E.s1 / E.h1; al[2] = 1.0 / E.h1;
+  be[0] = -(1.0 - E.s2) / E.h2; be[1] = -E.s2 / E.h2; be[2] = 1.0 / E.h2;
+}
 // ---- batched (block-diagonal over instances) least-squares assembly --------------------------
 // All instances are solved as ONE system: global vertex = instance vertex offset + mesh vertex.
 // A scene of 1000 instances then costs ~100 CG iterations of a few launches each instead of
@@ -857,7 +973,7 @@ __global__ void k_ls_topo(const uint64_t* __restrict__ keys, const uint32_t* __r
   topo[4ull * e + 3] = tris[3ull * (h1 / 3) + (h1 % 3 + 2) % 3];
 }
 // coefficients of the co-normal-derivative jump for every (instance, interior edge), world space
-__global__ void k_ls_edge_coeffs(const LsInst* __restrict__ inst, uint32_t n_inst, uint64_t NE, LsEdge* __restrict__ edges) {
+__global__ void k_ls_edge_coeffs(const LsInst* __restrict__ inst, uint32_t n_inst, uint64_t NE, int energy, LsEdge* __restrict__ edges) {
   const uint64_t ge = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (ge >= NE) return;
   const LsInst& I = inst[ls_find(n_inst, ge, [&](uint32_t m) { return inst[m].edge_begin; })];
@@ -865,31 +981,29 @@ __global__ void k_ls_edge_coeffs(const LsInst* __restrict__ inst, uint32_t n_ins
   LsEdge E;
   const uint32_t li = tp[0], lj = tp[1], lp = tp[2], lq = tp[3];
   E.i = li + I.vert_begin; E.j = lj + I.vert_begin; E.p = lp + I.vert_begin; E.q = lq + I.vert_begin;
-  E.c[0] = E.c[1] = E.c[2] = E.c[3] = 0.0;
+  E.s1 = E.s2 = 0.0; E.h1 = E.h2 = 1.0; E.c = -1.0; E.W = 0.0;
   auto W = [&](uint32_t v) { return xf_point(I.xf, v3(I.verts[3ull * v], I.verts[3ull * v + 1], I.verts[3ull * v + 2])); };
   const V3 pi = W(li), pj = W(lj), pp = W(lp), pq = W(lq);
   const double ex_ = (double)pj.x - pi.x, ey_ = (double)pj.y - pi.y, ez_ = (double)pj.z - pi.z;
   const double L2 = ex_ * ex_ + ey_ * ey_ + ez_ * ez_;
   if (L2 > 0.0) {
-    double s[2], h[2], A[2];
+    double s[2], h[2], A[2], r[2][3];
     const V3 opp[2] = {pp, pq};
 #pragma unroll
     for (int m = 0; m < 2; m++) {
       const double ox = (double)opp[m].x - pi.x, oy = (double)opp[m].y - pi.y, oz = (double)opp[m].z - pi.z;
       s[m] = (ox * ex_ + oy * ey_ + oz * ez_) / L2;
-      const double rx = ox - s[m] * ex_, ry = oy - s[m] * ey_, rz = oz - s[m] * ez_;
-      h[m] = sqrt(rx * rx + ry * ry + rz * rz);
+      r[m][0] = ox - s[m] * ex_; r[m][1] = oy - s[m] * ey_; r[m][2] = oz - s[m] * ez_;
+      h[m] = sqrt(r[m][0] * r[m][0] + r[m][1] * r[m][1] + r[m][2] * r[m][2]);
       A[m] = 0.5 * sqrt(L2) * h[m];
     }
     if (h[0] > 0.0 && h[1] > 0.0) {
-      const double w = A[0] + A[1];
-      E.c[0] = w * ((1.0 - s[0]) / h[0] + (1.0 - s[1]) / h[1]);
-      E.c[1] = w * (s[0] / h[0] + s[1] / h[1]);
-      E.c[2] = w * (-1.0 / h[0]);
-      E.c[3] = w * (-1.0 / h[1]);
+      E.s1 = s[0]; E.h1 = h[0]; E.s2 = s[1]; E.h2 = h[1];
+      if (energy == 1) { E.c = -1.0; E.W = (A[0] + A[1]) * (A[0] + A[1]); }
+      else { E.c = (r[0][0] * r[1][0] + r[0][1] * r[1][1] + r[0][2] * r[1][2]) / (h[0] * h[1]); E.W = A[0] + A[1]; }
     }
   }
-  edges[ge] = E;   // degenerate edges keep zero coefficients: a no-op in y = (M + wR) x
+  edges[ge] = E;   // degenerate edges keep W = 0: a no-op in y = (M + wR) x
 }
 
 // diagonal of the sampled mass matrix (lumped-mass test and the Jacobi preconditioner)
@@ -913,8 +1027,14 @@ __global__ void k_ls_diag_edges(const LsEdge* __restrict__ edges, uint32_t nE, d
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nE) return;
   const LsEdge E = edges[i];
-  atomicAdd(&diag[E.i], w * E.c[0] * E.c[0]); atomicAdd(&diag[E.j], w * E.c[1] * E.c[1]);
-  atomicAdd(&diag[E.p], w * E.c[2] * E.c[2]); atomicAdd(&diag[E.q], w * E.c[3] * E.c[3]);
+  if (E.W == 0.0) return;
+  double al[3], be[3];
+  ls_edge_coeffs(E, al, be);
+  const double ww = w * E.W;
+  atomicAdd(&diag[E.i], ww * (al[0] * al[0] + be[0] * be[0] - 2.0 * E.c * al[0] * be[0]));
+  atomicAdd(&diag[E.j], ww * (al[1] * al[1] + be[1] * be[1] - 2.0 * E.c * al[1] * be[1]));
+  atomicAdd(&diag[E.p], ww * al[2] * al[2]);
+  atomicAdd(&diag[E.q], ww * be[2] * be[2]);
 }
 // y += (M + w R) x   (y zeroed by the caller); one thread per triangle and per edge
 __global__ void k_ls_apply(const uint32_t* __restrict__ tris, uint64_t nT, const double* __restrict__ Mt, const LsEdge* __restrict__ edges,
@@ -933,57 +1053,102 @@ __global__ void k_ls_apply(const uint32_t* __restrict__ tris, uint64_t nT, const
   }
   if (i < nE) {
     const LsEdge E = edges[i];
-    const double J = E.c[0] * x[E.i] + E.c[1] * x[E.j] + E.c[2] * x[E.p] + E.c[3] * x[E.q];
-    const double wj = w * J;
-    atomicAdd(&y[E.i], wj * E.c[0]); atomicAdd(&y[E.j], wj * E.c[1]);
-    atomicAdd(&y[E.p], wj * E.c[2]); atomicAdd(&y[E.q], wj * E.c[3]);
+    if (E.W != 0.0) {
+      double al[3], be[3];
+      ls_edge_coeffs(E, al, be);
+      const double xi = x[E.i], xj = x[E.j];
+      const double a1 = al[0] * xi + al[1] * xj + al[2] * x[E.p], a2 = be[0] * xi + be[1] * xj + be[2] * x[E.q];
+      const double g1 = w * E.W * (a1 - E.c * a2), g2 = w * E.W * (a2 - E.c * a1);
+      atomicAdd(&y[E.i], g1 * al[0] + g2 * be[0]); atomicAdd(&y[E.j], g1 * al[1] + g2 * be[1]);
+      atomicAdd(&y[E.p], g1 * al[2]); atomicAdd(&y[E.q], g2 * be[2]);
+    }
   }
 }
-__global__ void k_ls_fix_apply(const uint8_t* __restrict__ fixed, const double* __restrict__ p, double* __restrict__ Ap, uint64_t nV) {
-  const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (v < nV && fixed[v]) Ap[v] += p[v];
+// ---- Jacobi-PCG pieces.  Scalars live on the device: S[0] = |b|^2, S[1] = r.z of the previous iteration, and two
+// banks S[4 + 4 k ...] (k = iteration parity) of {p.Ap, r.z, |r|^2} accumulators; the bank of the NEXT iteration is
+// zeroed by k_ls_dir, so an iteration is four launches with no memset, no copy and no host round trip (the host reads
+// |r|^2 every few iterations only). ----
+AOB_D double block_sum(double acc, double* sh) {   // all threads of a 256-thread block; result valid in thread 0
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  acc = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+  if (threadIdx.x < 32)
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  return acc;
 }
 // out[slot] += sum a[i]*b[i]  (block reduce + one fp64 atomic per block)
 __global__ void k_dot(const double* __restrict__ a, const double* __restrict__ b, uint64_t n, double* __restrict__ out) {
   __shared__ double sh[32];
   double acc = 0.0;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) acc += a[i] * b[i];
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    acc = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (threadIdx.x == 0) atomicAdd(out, acc);
-  }
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) atomicAdd(out, acc);
 }
-// z = r / diag ; p = z (init) ; scal[0] += r.z
+// anchored rows (decision #7): Ap += p there; then bank[0] += p.Ap
+__global__ void k_ls_pap(const uint8_t* __restrict__ fixed, const double* __restrict__ p, double* __restrict__ Ap, uint64_t nV, double* __restrict__ bank) {
+  __shared__ double sh[32];
+  double acc = 0.0;
+  for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nV; v += (uint64_t)gridDim.x * blockDim.x) {
+    const double pv = p[v];
+    double a = Ap[v];
+    if (fixed[v]) { a += pv; Ap[v] = a; }
+    acc += pv * a;
+  }
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) atomicAdd(&bank[0], acc);
+}
+// z = r / diag ; p = z (init) ; x = 0
 __global__ void k_ls_init(const double* __restrict__ rhs, const double* __restrict__ diag, double* __restrict__ r, double* __restrict__ z,
-                          double* __restrict__ p, double* __restrict__ x, uint64_t nV) {
+                          double* __restrict__ p, double* __restrict__ x, double* __restrict__ Ap, uint64_t nV) {
   const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= nV) return;
   x[v] = 0.0;
   r[v] = rhs[v];
   z[v] = rhs[v] / diag[v];
   p[v] = z[v];
+  Ap[v] = 0.0;
 }
-// x += alpha p ; r -= alpha Ap ; z = r/diag     (alpha = scal[rz]/scal[pAp] read on device)
-__global__ void k_ls_update(const double* __restrict__ scal, int i_rz, int i_pap, const double* __restrict__ p, const double* __restrict__ Ap,
-                            const double* __restrict__ diag, double* __restrict__ x, double* __restrict__ r, double* __restrict__ z, uint64_t nV) {
-  const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= nV) return;
-  const double alpha = scal[i_rz] / scal[i_pap];
-  x[v] += alpha * p[v];
-  const double rv = r[v] - alpha * Ap[v];
-  r[v] = rv;
-  z[v] = rv / diag[v];
+// x += alpha p ; r -= alpha Ap ; z = r/diag ; bank[1] += r.z ; bank[2] += |r|^2     (alpha = S[1] / bank[0])
+__global__ void k_ls_update(const double* __restrict__ S, const double* __restrict__ p, const double* __restrict__ Ap,
+                            const double* __restrict__ diag, double* __restrict__ x, double* __restrict__ r, double* __restrict__ z, uint64_t nV,
+                            double* bank) {
+  __shared__ double sh[32];
+  const double alpha = S[1] / bank[0];   // (bank[0] is complete: k_ls_pap ran before this launch)
+  double rz = 0.0, rr = 0.0;
+  for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nV; v += (uint64_t)gridDim.x * blockDim.x) {
+    x[v] += alpha * p[v];
+    const double rv = r[v] - alpha * Ap[v];
+    r[v] = rv;
+    const double zv = rv / diag[v];
+    z[v] = zv;
+    rz += rv * zv;
+    rr += rv * rv;
+  }
+  rz = block_sum(rz, sh);
+  __syncthreads();
+  rr = block_sum(rr, sh);
+  if (threadIdx.x == 0) { atomicAdd(&bank[1], rz); atomicAdd(&bank[2], rr); }
 }
-// p = z + beta p   (beta = scal[rz_new]/scal[rz_old])
-__global__ void k_ls_dir(const double* __restrict__ scal, int i_new, int i_old, const double* __restrict__ z, double* __restrict__ p, uint64_t nV) {
-  const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= nV) return;
-  const double beta = scal[i_new] / scal[i_old];
-  p[v] = z[v] + beta * p[v];
+// p = z + beta p ; Ap = 0 for the next product     (beta = bank[1] / S[1]); the last block to finish rotates the
+// scalars: S[1] <- bank[1], S[2] <- bank[2] (|r|^2 for the host), S[3] <- bank[0] (p.Ap, breakdown check), and zeroes the other bank
+__global__ void k_ls_dir(double* __restrict__ S, double* __restrict__ bank, double* __restrict__ other_bank, const double* __restrict__ z,
+                         double* __restrict__ p, double* __restrict__ Ap, uint64_t nV, unsigned int* __restrict__ done_blocks) {
+  const double beta = bank[1] / S[1];
+  for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nV; v += (uint64_t)gridDim.x * blockDim.x) {
+    p[v] = z[v] + beta * p[v];
+    Ap[v] = 0.0;
+  }
+  __syncthreads();   // every thread of the block has read S[1] and bank[1]
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(done_blocks, 1u) == gridDim.x - 1) {   // all blocks have read the scalars
+      S[3] = bank[0]; S[2] = bank[2]; S[1] = bank[1];
+      other_bank[0] = other_bank[1] = other_bank[2] = 0.0;
+      *done_blocks = 0u;
+      __threadfence();
+    }
+  }
 }
 __global__ void k_d2f(const double* __restrict__ x, float* __restrict__ out, uint64_t n) {
   const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

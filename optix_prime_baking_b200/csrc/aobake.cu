@@ -297,16 +297,39 @@ int build_segment(AoBake* ctx, const F4* d_plo, const F4* d_phi, uint32_t n, uin
   k_init_bounds<<<1, 32, 0, st>>>(d_b.p + 6);
   k_bounds<<<std::min<unsigned>(grid_for(n, 256), 148u * 8u), 256, 0, st>>>(d_plo, d_phi, n, d_b.p, d_b.p + 6);
   k_decode_bounds<<<1, 32, 0, st>>>(d_b.p + 6, d_box.p);
-  k_morton<<<grid_for(n, 256), 256, 0, st>>>(d_plo, d_phi, n, d_b.p, keys.p, vals.p);
+  // oversized primitives stay out of the tree (see k_flag_big): at most 7 leaf slots of the extra root
+  DBuf<uint8_t> big;
+  DBuf<uint32_t> big_count;
+  DBuf<int> d_bs;   // centroid + box bounds of the ordinary primitives
+  CK(big.alloc(n)); CK(big_count.alloc(1)); CK(d_bs.alloc(12));
+  CK(cudaMemsetAsync(big_count.p, 0, sizeof(uint32_t), st));
+  k_flag_big<<<grid_for(n, 256), 256, 0, st>>>(d_plo, d_phi, n, d_b.p + 6, big.p, big_count.p);
+  CKL();
+  uint32_t n_big = 0;
+  CK(cudaMemcpyAsync(&n_big, big_count.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const uint32_t per_slot = std::max(1u, std::min(max_leaf, 3u));
+  const bool split = ctx->params.no_oversized_split == 0 && n_big > 0 && n_big < n && n_big <= 7u * per_slot;
+  const uint32_t n_small = split ? n - n_big : n;
+  if (split) {
+    k_init_bounds<<<1, 32, 0, st>>>(d_bs.p);
+    k_init_bounds<<<1, 32, 0, st>>>(d_bs.p + 6);
+    k_bounds_small<<<grid_for(n, 256), 256, 0, st>>>(d_plo, d_phi, big.p, n, d_bs.p, d_bs.p + 6);
+    k_morton_small<<<grid_for(n, 256), 256, 0, st>>>(d_plo, d_phi, big.p, n, d_bs.p, keys.p, vals.p);
+  } else {
+    k_morton<<<grid_for(n, 256), 256, 0, st>>>(d_plo, d_phi, n, d_b.p, keys.p, vals.p);
+  }
   CKL();
   {
     size_t tmp_bytes = 0;
-    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.p, keys_s.p, vals.p, vals_s.p, (int)n, 0, 63, st));
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.p, keys_s.p, vals.p, vals_s.p, (int)n, 0, 64, st));
     DBuf<uint8_t> tmp;
     CK(tmp.alloc(tmp_bytes));
-    CK(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys.p, keys_s.p, vals.p, vals_s.p, (int)n, 0, 63, st));
+    CK(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys.p, keys_s.p, vals.p, vals_s.p, (int)n, 0, 64, st));
     CK(cudaStreamSynchronize(st));
   }
+  const uint32_t n_all = n;
+  n = n_small;   // the tree below is built over the ordinary primitives only (all of them when nothing was split off)
   Lbvh L;
   L.keys = keys_s.p; L.prim = vals_s.p; L.plo = d_plo; L.phi = d_phi;
   L.left = left.p; L.right = right.p; L.first = first.p; L.last = last.p;
@@ -340,6 +363,15 @@ int build_segment(AoBake* ctx, const F4* d_plo, const F4* d_phi, uint32_t n, uin
   if (hc[1] != n) return ctx->fail(AOBAKE_ERR_CUDA, "BVH collapse emitted %u of %u primitives", hc[1], n);
   out->node_count = hc[0];
   out->levels = levels;
+  if (split) {
+    // one extra root on top: [tree over the ordinary primitives | oversized primitives as leaf slots]
+    k_super_root<<<1, 32, 0, st>>>(d_nodes, node_offset + hc[0], node_offset, d_b.p + 6, d_bs.p + 6, d_plo, d_phi, vals_s.p, n_small, n_all - n_small,
+                                   per_slot, prim_offset, d_leaf_prims);
+    CKL();
+    out->root = node_offset + hc[0];
+    out->node_count = hc[0] + 1;
+    out->levels = levels + 1;
+  }
   CK(cudaMemcpyAsync(out->box, d_box.p, sizeof(out->box), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return AOBAKE_OK;
@@ -466,7 +498,7 @@ int aobake_default_params(AoBakeParams* p) {
   memset(p, 0, sizeof(*p));
   p->device = 0;
   p->instancing_mode = AOBAKE_INSTANCING_AUTO;
-  p->cg_max_iterations = 2000;
+  p->cg_max_iterations = 20000;
   p->cg_tolerance = 1e-6f;
   p->trace_kernel = 0;
   p->collect_stats = 0;
@@ -475,6 +507,8 @@ int aobake_default_params(AoBakeParams* p) {
   p->node_test = 0;
   p->deferred_capacity = 0;
   p->tri_batch = 0;
+  p->no_oversized_split = 0;
+  p->ls_energy = 0;
   return AOBAKE_OK;
 }
 
@@ -680,7 +714,7 @@ static int set_scene_impl(AoBake* ctx, const AoScene* scene, const AoScene* bloc
     CK(cudaMemcpyAsync(ctx->d_nodes.p, nodes.p, seg.node_count * sizeof(Node8), cudaMemcpyDeviceToDevice, st));
     CK(cudaStreamSynchronize(st));
     ctx->d_insts.release();
-    ctx->root = 0;
+    ctx->root = seg.root;
     ctx->scene_diag = n ? sqrtf((seg.box[3] - seg.box[0]) * (seg.box[3] - seg.box[0]) + (seg.box[4] - seg.box[1]) * (seg.box[4] - seg.box[1]) +
                                 (seg.box[5] - seg.box[2]) * (seg.box[5] - seg.box[2])) : 0.f;
     ctx->stats.num_bvh_nodes = seg.node_count;
@@ -1349,7 +1383,7 @@ int ls_filter_batched(AoBake* ctx, float weight, uint32_t ib, uint32_t ie, DBuf<
   DBuf<uint8_t> fixed;
   DBuf<LsEdge> edges;
   CK(d_inst.alloc(std::max(nI, 1u))); CK(gtris.alloc(3 * t1)); CK(Mt.alloc(6 * t1)); CK(rhs.alloc(v1)); CK(diag.alloc(v1));
-  CK(x.alloc(v1)); CK(r.alloc(v1)); CK(z.alloc(v1)); CK(p.alloc(v1)); CK(Ap.alloc(v1)); CK(scal.alloc(8)); CK(fixed.alloc(v1));
+  CK(x.alloc(v1)); CK(r.alloc(v1)); CK(z.alloc(v1)); CK(p.alloc(v1)); CK(Ap.alloc(v1)); CK(scal.alloc(12)); CK(fixed.alloc(v1));
   CK(edges.alloc(std::max<uint64_t>(NE, 1))); CK(d_out.alloc(v1));
   if (nI) CK(cudaMemcpyAsync(d_inst.p, h.data(), nI * sizeof(LsInst), cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(Mt.p, 0, Mt.n * sizeof(double), st));
@@ -1357,21 +1391,25 @@ int ls_filter_batched(AoBake* ctx, float weight, uint32_t ib, uint32_t ie, DBuf<
   CK(cudaMemsetAsync(diag.p, 0, v1 * sizeof(double), st));
   if (NT) k_ls_gtris<<<grid_for(NT, 256), 256, 0, st>>>(d_inst.p, nI, NT, gtris.p);
   if (NS) k_ls_mass_b<<<grid_for(NS, 256), 256, 0, st>>>(ctx->d_info.p + S0, ctx->d_ao.p + S0, NS, d_inst.p, nI, gtris.p, Mt.p, rhs.p);
-  if (NE) k_ls_edge_coeffs<<<grid_for(NE, 256), 256, 0, st>>>(d_inst.p, nI, NE, edges.p);
+  if (NE) k_ls_edge_coeffs<<<grid_for(NE, 256), 256, 0, st>>>(d_inst.p, nI, NE, ctx->params.ls_energy, edges.p);
   if (NT) k_ls_diag_mass<<<grid_for(NT, 256), 256, 0, st>>>(gtris.p, NT, Mt.p, diag.p);
   if (NV) k_ls_fix<<<grid_for(NV, 256), 256, 0, st>>>(diag.p, rhs.p, fixed.p, NV);
   if (NE) k_ls_diag_edges<<<grid_for(NE, 256), 256, 0, st>>>(edges.p, (uint32_t)NE, w, diag.p);
-  if (NV) k_ls_init<<<grid_for(NV, 256), 256, 0, st>>>(rhs.p, diag.p, r.p, z.p, p.p, x.p, NV);
+  if (NV) k_ls_init<<<grid_for(NV, 256), 256, 0, st>>>(rhs.p, diag.p, r.p, z.p, p.p, x.p, Ap.p, NV);
   CKL();
-  // scal: [0]=|b|^2 [1]=rz_old [2]=pAp [3]=rz_new [4]=|r|^2
-  const unsigned dot_grid = std::min<unsigned>(grid_for(v1, 256), (unsigned)ctx->sm_count * 8u);
+  // scal: [0] = |b|^2, [1] = r.z of the previous iteration, [2] = |r|^2 and [3] = p.Ap of the last finished iteration,
+  // [4..6] and [8..10] = the two accumulator banks {p.Ap, r.z, |r|^2} (iteration parity)
+  const unsigned vec_grid = std::min<unsigned>(grid_for(v1, 256), (unsigned)ctx->sm_count * 8u);
   const uint64_t nwork = std::max<uint64_t>(NT, NE);
-  CK(cudaMemsetAsync(scal.p, 0, 8 * sizeof(double), st));
+  DBuf<unsigned int> done_blocks;
+  CK(done_blocks.alloc(1));
+  CK(cudaMemsetAsync(done_blocks.p, 0, sizeof(unsigned int), st));
+  CK(cudaMemsetAsync(scal.p, 0, 12 * sizeof(double), st));
   if (NV) {
-    k_dot<<<dot_grid, 256, 0, st>>>(rhs.p, rhs.p, NV, scal.p + 0);
-    k_dot<<<dot_grid, 256, 0, st>>>(r.p, z.p, NV, scal.p + 1);
+    k_dot<<<vec_grid, 256, 0, st>>>(rhs.p, rhs.p, NV, scal.p + 0);
+    k_dot<<<vec_grid, 256, 0, st>>>(r.p, z.p, NV, scal.p + 1);
   }
-  double hs[8];
+  double hs[4];
   CK(cudaMemcpyAsync(hs, scal.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   const double bnorm2 = hs[0];
@@ -1379,22 +1417,23 @@ int ls_filter_batched(AoBake* ctx, float weight, uint32_t ib, uint32_t ie, DBuf<
   if (NV && bnorm2 > 0.0) {
     const double tol2 = (double)ctx->params.cg_tolerance * (double)ctx->params.cg_tolerance * bnorm2;
     double rr = bnorm2;
-    for (; it < ctx->params.cg_max_iterations && rr > tol2; it++) {
-      CK(cudaMemsetAsync(Ap.p, 0, NV * sizeof(double), st));
-      CK(cudaMemsetAsync(scal.p + 2, 0, 3 * sizeof(double), st));
-      if (nwork) k_ls_apply<<<grid_for(nwork, 256), 256, 0, st>>>(gtris.p, NT, Mt.p, edges.p, (uint32_t)NE, w, p.p, Ap.p);
-      k_ls_fix_apply<<<grid_for(NV, 256), 256, 0, st>>>(fixed.p, p.p, Ap.p, NV);
-      k_dot<<<dot_grid, 256, 0, st>>>(p.p, Ap.p, NV, scal.p + 2);
-      k_ls_update<<<grid_for(NV, 256), 256, 0, st>>>(scal.p, 1, 2, p.p, Ap.p, diag.p, x.p, r.p, z.p, NV);
-      k_dot<<<dot_grid, 256, 0, st>>>(r.p, z.p, NV, scal.p + 3);
-      k_dot<<<dot_grid, 256, 0, st>>>(r.p, r.p, NV, scal.p + 4);
-      k_ls_dir<<<grid_for(NV, 256), 256, 0, st>>>(scal.p, 3, 1, z.p, p.p, NV);
+    // the host looks at |r|^2 every kCheck iterations: up to kCheck - 1 iterations past the tolerance, no round trip per iteration
+    constexpr int kCheck = 8;
+    while (it < ctx->params.cg_max_iterations && rr > tol2) {
+      const int burst = std::min(kCheck, ctx->params.cg_max_iterations - it);
+      for (int k = 0; k < burst; k++, it++) {
+        double* bank = scal.p + 4 + 4 * (it & 1);
+        double* other = scal.p + 4 + 4 * ((it + 1) & 1);
+        if (nwork) k_ls_apply<<<grid_for(nwork, 256), 256, 0, st>>>(gtris.p, NT, Mt.p, edges.p, (uint32_t)NE, w, p.p, Ap.p);
+        k_ls_pap<<<vec_grid, 256, 0, st>>>(fixed.p, p.p, Ap.p, NV, bank);
+        k_ls_update<<<vec_grid, 256, 0, st>>>(scal.p, p.p, Ap.p, diag.p, x.p, r.p, z.p, NV, bank);
+        k_ls_dir<<<vec_grid, 256, 0, st>>>(scal.p, bank, other, z.p, p.p, Ap.p, NV, done_blocks.p);
+      }
       CKL();
       CK(cudaMemcpyAsync(hs, scal.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
-      if (!(hs[2] > 0.0)) return ctx->fail(AOBAKE_ERR_SOLVER, "CG breakdown: p.Ap = %g at iteration %d", hs[2], it);
-      rr = hs[4];
-      CK(cudaMemcpyAsync(scal.p + 1, scal.p + 3, sizeof(double), cudaMemcpyDeviceToDevice, st));
+      if (!(hs[3] > 0.0)) return ctx->fail(AOBAKE_ERR_SOLVER, "CG breakdown: p.Ap = %g near iteration %d", hs[3], it);
+      rr = hs[2];
     }
     if (rr > tol2) return ctx->fail(AOBAKE_ERR_SOLVER, "CG did not reach %g in %d iterations (|r|/|b| = %g)", (double)ctx->params.cg_tolerance, it, sqrt(rr / bnorm2));
   } else if (NV) {

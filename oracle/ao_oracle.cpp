@@ -953,17 +953,27 @@ int ao_oracle_filter_area(const OrScene* sc, const uint64_t* per_instance, const
 }
 
 // bake_filter_least_squares.cpp — SURVEY a16, decisions #6/#7: solve (M + w R) x = b in
-// fp64 per instance.  M = sum_samples dA b b^T, b = sum dA ao b.  R = sum over interior
-// edges (A1+A2)^2 J^T J where J x is the jump of the co-normal derivative of the
-// piecewise-linear interpolant across the edge (intrinsic/unfolded form):
-//   J = [(1-s1)/h1 + (1-s2)/h2] x_i + [s1/h1 + s2/h2] x_j - x_p/h1 - x_q/h2
-// (i,j) edge ends, p/q opposite vertices, h = altitude of the opposite vertex, s = foot
-// parameter along the edge.  Geometry uses world-space vertices.  Vertices with zero lumped
-// mass get M_vv = 1, rhs 0 (decision #7).  Solver: Jacobi-preconditioned CG from x = 0 to
-// |r|/|b| <= tol.  Returns iterations used (>= 0) or < 0 on error.
-struct LsEdge { uint32_t i, j, p, q; double c[4]; };
+// fp64 per instance.  M = sum_samples dA b b^T, b = sum dA ao b.  R = sum over interior edges of the
+// energy of the gradient jump of the piecewise-linear interpolant across the edge (Kavan, Bargteil,
+// Sloan 2011, "Least Squares Vertex Baking"):
+//   E_edge = (A1 + A2) * |grad(T1) - grad(T2)|^2      (all three components of the 3-D gradients)
+// With (i,j) the edge ends, p/q the opposite vertices, h the altitude of the opposite vertex, s its foot
+// parameter along the edge and m1, m2 the unit in-plane normals of the edge pointing at p and q:
+//   grad(T1) - grad(T2) = a1 m1 - a2 m2,   a1 = (x_p - s1 x_j - (1-s1) x_i) / h1,   a2 likewise with q
+// (the components along the edge cancel), so  |.|^2 = a1^2 + a2^2 - 2 c a1 a2  with c = m1 . m2
+// (c = -1 for a flat pair: the energy is then (a1 + a2)^2, the squared jump of the co-normal derivative).
+// energy = 1 selects the round-1 form instead: (A1 + A2)^2 (a1 + a2)^2 — the unfolded jump with the area
+// squared, which makes w scale-free; kept as an option (AoBakeParams::ls_energy = 1 on the GPU side).
+// Geometry uses world-space vertices.  Vertices with zero lumped mass get M_vv = 1, rhs 0 (decision #7).
+// Solver: Jacobi-preconditioned CG from x = 0 to |r|/|b| <= tol.  Returns iterations used (>= 0) or < 0.
+struct LsEdge { uint32_t i, j, p, q; double s1, h1, s2, h2, c, W; };
+// y += w * dE/dx for one edge; returns nothing.  a1 = al . x on (i,j,p), a2 = be . x on (i,j,q).
+static inline void ls_edge_coeffs(const LsEdge& E, double al[3], double be[3]) {
+  al[0] = -(1.0 - E.s1) / E.h1; al[1] = -E.s1 / E.h1; al[2] = 1.0 / E.h1;
+  be[0] = -(1.0 - E.s2) / E.h2; be[1] = -E.s2 / E.h2; be[2] = 1.0 / E.h2;
+}
 
-static void ls_build_edges(const OrMesh& m, const float* xf, std::vector<LsEdge>& edges) {
+static void ls_build_edges(const OrMesh& m, const float* xf, int energy, std::vector<LsEdge>& edges) {
   struct Half { uint64_t key; uint32_t tri; uint32_t opp; };
   std::vector<Half> hs;
   hs.reserve(3 * m.num_triangles);
@@ -988,22 +998,20 @@ static void ls_build_edges(const OrMesh& m, const float* xf, std::vector<LsEdge>
       V3 pp = xf_point(xf, load3(vertex_ptr(m, E.p))), pq = xf_point(xf, load3(vertex_ptr(m, E.q)));
       double ex = (double)pj.x - pi.x, ey = (double)pj.y - pi.y, ez = (double)pj.z - pi.z;
       double L2 = ex * ex + ey * ey + ez * ez;
-      auto foot = [&](V3 o, double* s, double* h, double* area) {
+      double r1[3], r2[3];
+      auto foot = [&](V3 o, double* s, double* h, double* area, double* r) {
         double ox = (double)o.x - pi.x, oy = (double)o.y - pi.y, oz = (double)o.z - pi.z;
         *s = (ox * ex + oy * ey + oz * ez) / L2;
-        double rx = ox - *s * ex, ry = oy - *s * ey, rz = oz - *s * ez;
-        *h = std::sqrt(rx * rx + ry * ry + rz * rz);
+        r[0] = ox - *s * ex; r[1] = oy - *s * ey; r[2] = oz - *s * ez;
+        *h = std::sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
         *area = 0.5 * std::sqrt(L2) * *h;
       };
-      double s1, h1, A1, s2, h2, A2;
+      double A1 = 0, A2 = 0;
       bool ok = L2 > 0.0;
-      if (ok) { foot(pp, &s1, &h1, &A1); foot(pq, &s2, &h2, &A2); ok = h1 > 0.0 && h2 > 0.0; }
+      if (ok) { foot(pp, &E.s1, &E.h1, &A1, r1); foot(pq, &E.s2, &E.h2, &A2, r2); ok = E.h1 > 0.0 && E.h2 > 0.0; }
       if (ok) {
-        double w = A1 + A2;
-        E.c[0] = w * ((1.0 - s1) / h1 + (1.0 - s2) / h2);
-        E.c[1] = w * (s1 / h1 + s2 / h2);
-        E.c[2] = w * (-1.0 / h1);
-        E.c[3] = w * (-1.0 / h2);
+        if (energy == 1) { E.c = -1.0; E.W = (A1 + A2) * (A1 + A2); }
+        else { E.c = (r1[0] * r2[0] + r1[1] * r2[1] + r1[2] * r2[2]) / (E.h1 * E.h2); E.W = A1 + A2; }
         edges.push_back(E);
       }
     }
@@ -1011,11 +1019,14 @@ static void ls_build_edges(const OrMesh& m, const float* xf, std::vector<LsEdge>
   }
 }
 
-int ao_oracle_filter_least_squares(const OrScene* sc, const uint64_t* per_instance, const OrSamples* S,
-                                   const float* ao, float weight, double tol, int max_iter,
-                                   float** vertex_ao) {
+// check_only: vertex_ao holds a candidate solution; nothing is solved, *relres receives
+// max over instances of |b - (M + wR) x| / |b| under THIS file's operator (full-size parity checks, where
+// a CPU solve of the same system would take minutes).
+static int ls_impl(const OrScene* sc, const uint64_t* per_instance, const OrSamples* S, const float* ao, float weight, double tol,
+                   int max_iter, float** vertex_ao, int energy, bool check_only, double* relres) {
   uint64_t base = 0;
   int total_iters = 0;
+  if (relres) *relres = 0.0;
   for (uint64_t inst = 0; inst < sc->num_instances; inst++) {
     const OrInstance& I = sc->instances[inst];
     const OrMesh& m = sc->meshes[I.mesh_index];
@@ -1033,7 +1044,7 @@ int ao_oracle_filter_least_squares(const OrScene* sc, const uint64_t* per_instan
       b[idx[0]] += dA * a * b0; b[idx[1]] += dA * a * b1; b[idx[2]] += dA * a * b2;
     }
     std::vector<LsEdge> edges;
-    if (weight != 0.0f) ls_build_edges(m, I.xform, edges);
+    if (weight != 0.0f) ls_build_edges(m, I.xform, energy, edges);
     const double w = weight;
     auto apply = [&](const std::vector<double>& x, std::vector<double>& y) {
       std::fill(y.begin(), y.end(), 0.0);
@@ -1046,9 +1057,13 @@ int ao_oracle_filter_least_squares(const OrScene* sc, const uint64_t* per_instan
         y[idx[2]] += M[2] * x0 + M[4] * x1 + M[5] * x2;
       }
       for (const LsEdge& E : edges) {
-        double J = E.c[0] * x[E.i] + E.c[1] * x[E.j] + E.c[2] * x[E.p] + E.c[3] * x[E.q];
-        double wj = w * J;
-        y[E.i] += wj * E.c[0]; y[E.j] += wj * E.c[1]; y[E.p] += wj * E.c[2]; y[E.q] += wj * E.c[3];
+        double al[3], be[3];
+        ls_edge_coeffs(E, al, be);
+        const double a1 = al[0] * x[E.i] + al[1] * x[E.j] + al[2] * x[E.p];
+        const double a2 = be[0] * x[E.i] + be[1] * x[E.j] + be[2] * x[E.q];
+        const double g1 = w * E.W * (a1 - E.c * a2), g2 = w * E.W * (a2 - E.c * a1);   // R x = half the gradient of x^T R x = W (a1^2 + a2^2 - 2 c a1 a2)
+        y[E.i] += g1 * al[0] + g2 * be[0]; y[E.j] += g1 * al[1] + g2 * be[1];
+        y[E.p] += g1 * al[2]; y[E.q] += g2 * be[2];
       }
     };
     for (uint64_t t = 0; t < nT; t++) {
@@ -1062,13 +1077,29 @@ int ao_oracle_filter_least_squares(const OrScene* sc, const uint64_t* per_instan
     for (uint64_t v = 0; v < nV; v++)
       if (!(diag[v] > 0.0)) { fixed[v] = 1; diag[v] = 1.0; b[v] = 0.0; }
     for (const LsEdge& E : edges) {
-      diag[E.i] += w * E.c[0] * E.c[0]; diag[E.j] += w * E.c[1] * E.c[1];
-      diag[E.p] += w * E.c[2] * E.c[2]; diag[E.q] += w * E.c[3] * E.c[3];
+      double al[3], be[3];
+      ls_edge_coeffs(E, al, be);
+      diag[E.i] += w * E.W * (al[0] * al[0] + be[0] * be[0] - 2.0 * E.c * al[0] * be[0]);
+      diag[E.j] += w * E.W * (al[1] * al[1] + be[1] * be[1] - 2.0 * E.c * al[1] * be[1]);
+      diag[E.p] += w * E.W * al[2] * al[2];
+      diag[E.q] += w * E.W * be[2] * be[2];
     }
     std::vector<double> x(nV, 0.0), r(b), z(nV), p(nV), Ap(nV);
     double bnorm = 0.0;
     for (uint64_t v = 0; v < nV; v++) bnorm += b[v] * b[v];
     bnorm = std::sqrt(bnorm);
+    if (check_only) {
+      for (uint64_t v = 0; v < nV; v++) x[v] = vertex_ao[inst][v];
+      apply(x, Ap);
+      double rn = 0.0;
+      for (uint64_t v = 0; v < nV; v++) {
+        const double rv = b[v] - (Ap[v] + (fixed[v] ? x[v] : 0.0));
+        rn += rv * rv;
+      }
+      if (relres && bnorm > 0.0) *relres = std::max(*relres, std::sqrt(rn) / bnorm);
+      base += per_instance[inst];
+      continue;
+    }
     int it = 0;
     if (bnorm > 0.0) {
       double rz = 0.0;
@@ -1097,6 +1128,20 @@ int ao_oracle_filter_least_squares(const OrScene* sc, const uint64_t* per_instan
     base += per_instance[inst];
   }
   return total_iters;
+}
+
+int ao_oracle_filter_least_squares(const OrScene* sc, const uint64_t* per_instance, const OrSamples* S,
+                                   const float* ao, float weight, double tol, int max_iter,
+                                   float** vertex_ao, int energy) {
+  return ls_impl(sc, per_instance, S, ao, weight, tol, max_iter, vertex_ao, energy, false, nullptr);
+}
+
+// Relative residual of a candidate least-squares solution under the oracle's operator (see ls_impl).
+double ao_oracle_ls_residual(const OrScene* sc, const uint64_t* per_instance, const OrSamples* S, const float* ao, float weight,
+                             float** vertex_x, int energy) {
+  double res = 0.0;
+  ls_impl(sc, per_instance, S, ao, weight, 0.0, 0, vertex_x, energy, true, &res);
+  return res;
 }
 
 }  // extern "C"

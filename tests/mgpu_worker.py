@@ -13,6 +13,15 @@ from optix_prime_baking_b200 import api, scenes  # noqa: E402
 from optix_prime_baking_b200.multi_gpu import DistributedBaker  # noqa: E402
 
 
+def _fresh_id(rank):
+    """A new NCCL unique id from rank 0, shipped over torch.distributed (one id per communicator)."""
+    t = torch.zeros(128, dtype=torch.uint8, device='cuda')
+    if rank == 0:
+        t.copy_(torch.frombuffer(bytearray(api.Baker.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(t, src=0)
+    return t.cpu().numpy().tobytes()
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -23,7 +32,7 @@ def main():
         with api.Baker(device=local) as bk:
             bk.set_scene(scene, blockers)
             total, per = bk.distribute_samples(2, 10007)
-            bk.sample_instances(per, 2, download=False)
+            sb_host = bk.sample_instances(per, 2, download=True)
             ao_c = DistributedBaker(bk, rank, world, local).compute_ao(64, off, maxd, gather=True, download=True, interleave=False)
             ao = DistributedBaker(bk, rank, world, local).compute_ao(64, off, maxd, gather=True, download=True, interleave=True,
                                                                       block_samples=2048)
@@ -35,11 +44,23 @@ def main():
             dist.broadcast(idt, src=0)
             bk.comm_init(rank, world, bytes(idt.cpu().numpy().tobytes()))
             ao_native = bk.compute_ao_distributed(64, off, maxd)
+            # host-buffer forms: 1/N of the scene per rank + all-gather, only the owned sample super-blocks uploaded
+            with api.Baker(device=local) as b2:
+                b2.comm_init(rank, world, _fresh_id(rank))
+                b2.set_scene(scene, blockers, distributed=True)
+                b2.set_samples(sb_host, per, distributed=True)
+                ao_host = b2.compute_ao_distributed(64, off, maxd)
+                v_host = b2.map_ao_to_vertices(api.FILTER_AREA_BASED, distributed=True)
+                b2.comm_destroy()
+            assert np.array_equal(ao_host.view(np.uint32), ao_native.view(np.uint32)), 'set_scene/set_samples_distributed path differs'
+
             v_dist = bk.map_ao_to_vertices(api.FILTER_LEAST_SQUARES, 0.1, distributed=True)   # instances split over the ranks
             v_repl = bk.map_ao_to_vertices(api.FILTER_LEAST_SQUARES, 0.1)
             for a, b in zip(v_dist, v_repl):
                 assert np.abs(a - b).max() < 1e-4, 'distributed vertex map differs from the replicated one'
             va_dist = bk.map_ao_to_vertices(api.FILTER_AREA_BASED, distributed=True)
+            for a, b in zip(v_host, va_dist):
+                assert np.abs(a - b).max() < 1e-6
             bk.comm_destroy()
             assert np.array_equal(ao_native.view(np.uint32), ao.view(np.uint32)), 'native NCCL exchange differs'
             v_area = bk.map_ao_to_vertices(api.FILTER_AREA_BASED)

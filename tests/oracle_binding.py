@@ -49,7 +49,9 @@ def lib():
                                            C.c_float, C.c_void_p, C.c_void_p]
         L.ao_oracle_filter_area.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ao_oracle_filter_least_squares.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
-                                                     C.c_double, C.c_int, C.c_void_p]
+                                                     C.c_double, C.c_int, C.c_void_p, C.c_int]
+        L.ao_oracle_ls_residual.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int]
+        L.ao_oracle_ls_residual.restype = C.c_double
         L.ao_oracle_instance_areas.argtypes = [C.c_void_p, C.c_void_p]
         L.ao_oracle_make_ground_plane.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float,
                                                   C.c_void_p, C.c_void_p]
@@ -174,15 +176,24 @@ class Oracle:
         return arrs
 
     def filter_least_squares(self, samples: SampleBuffers, ao: np.ndarray, weight=0.1, tol=1e-10,
-                             max_iter=20000, per_instance=None):
+                             max_iter=20000, per_instance=None, energy=0):
+        """energy 0: (A1+A2) |grad jump|^2 (SURVEY §9 #6, the default); 1: the scale-free round-1 form."""
         per = np.ascontiguousarray(self.per_instance if per_instance is None else per_instance, dtype=np.uint64)
         arrs, ptrs = _vertex_out(self.scene)
         ao = np.ascontiguousarray(ao, dtype=np.float32)
         iters = lib().ao_oracle_filter_least_squares(self.ps.ref(), per.ctypes.data, samples.ref(), ao.ctypes.data,
-                                                     float(weight), float(tol), int(max_iter), ptrs)
+                                                     float(weight), float(tol), int(max_iter), ptrs, int(energy))
         assert iters >= 0
         self.ls_iterations = iters
         return arrs
+
+    def ls_residual(self, samples: SampleBuffers, ao: np.ndarray, vertex_x, weight=0.1, per_instance=None, energy=0) -> float:
+        """|b - (M + wR) x| / |b| of a candidate solution (one array per instance) under the oracle's operator."""
+        per = np.ascontiguousarray(self.per_instance if per_instance is None else per_instance, dtype=np.uint64)
+        xs = [np.ascontiguousarray(v, dtype=np.float32) for v in vertex_x]
+        ptrs = (C.c_void_p * max(len(xs), 1))(*[a.ctypes.data for a in xs])
+        ao = np.ascontiguousarray(ao, dtype=np.float32)
+        return float(lib().ao_oracle_ls_residual(self.ps.ref(), per.ctypes.data, samples.ref(), ao.ctypes.data, float(weight), ptrs, int(energy)))
 
     def close(self):
         if self._tracer is not None:

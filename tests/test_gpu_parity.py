@@ -490,3 +490,47 @@ def test_fuzz_triangle_soups_match_brute_force(api, scale, offset, seed):
         got = bk.trace_rays(rays)
     assert 0.01 < want.mean() < 0.99
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("name", ["sphere_ground", "warped_ground", "instanced"])
+def test_oversized_primitives_hang_off_an_extra_root(api, name):
+    """A ground-plane quad (two triangles spanning 100 x the scene) under a fine mesh, and the same quad as a
+    huge instance in a TLAS: kept out of the tree, the hit counts are identical to the one-tree build and
+    the traversal visits fewer nodes."""
+    scene, blockers = SCENES[name]
+    off, maxd = scenes.default_distances(scene)
+    res = {}
+    for split_off in (False, True):
+        with api.Baker(trace_kernel=2, collect_stats=True, no_oversized_split=split_off) as bk:
+            bk.set_scene(scene, blockers)
+            total, per = bk.distribute_samples(2, 0)
+            bk.sample_instances(per, 2, download=False)
+            bk.compute_ao(64, off, maxd, download=False)
+            st = bk.stats()
+            res[split_off] = (bk.hit_counts(), st.node_visits / st.rays)
+    assert np.array_equal(res[False][0], res[True][0])
+    assert res[False][1] < res[True][1]               # fewer node visits per ray with the extra root
+
+
+def test_many_large_triangles_stay_in_the_tree(api):
+    """More oversized primitives than the extra root can hold (a coarse box room around a small sphere): the
+    builder falls back to one tree; brute-force parity either way."""
+    rng = np.random.default_rng(21)
+    quads = []
+    for k in range(10):   # 20 scene-sized triangles
+        a = rng.uniform(-50, 50, size=(4, 3)).astype(np.float32)
+        quads.append(a)
+    v = np.concatenate(quads + [scenes.uv_sphere(12, 12).vertices])
+    t = np.concatenate([np.array([[0, 1, 2], [0, 2, 3]], dtype=np.uint32) + 4 * k for k in range(10)] +
+                       [scenes.uv_sphere(12, 12).tris + 40])
+    scene = Scene([Mesh(v, t)], [Instance(0)])
+    orc = Oracle(scene, Scene([], []))
+    with api.Baker() as bk:
+        bk.set_scene(scene)
+        o = rng.uniform(-2, 2, size=(4000, 3)).astype(np.float32)
+        d = rng.normal(size=(4000, 3)).astype(np.float32)
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        rays = np.concatenate([o, np.zeros((4000, 1), np.float32), d, np.full((4000, 1), 1e4, np.float32)], axis=1)
+        got = bk.trace_rays(rays)
+    want = orc.trace_rays(rays, brute=True)
+    check_hits(orc, rays, got, want)

@@ -261,7 +261,7 @@ def test_any_hit_against_fp64_moller_trumbore():
 
 
 # ---- a15/a16: vertex maps, dense fp64 -----------------------------------------------------------
-def _dense_least_squares(mesh: Mesh, xform, infos, ao, weight):
+def _dense_least_squares(mesh: Mesh, xform, infos, ao, weight, energy=0):
     nV = len(mesh.vertices)
     M = np.zeros((nV, nV))
     b = np.zeros(nV)
@@ -290,10 +290,11 @@ def _dense_least_squares(mesh: Mesh, xform, infos, ao, weight):
             continue
         (_, p), (_, q) = sorted(lst)[:2]
         e = W[j] - W[i]
-        row = np.zeros(nV)
+        row = np.zeros(nV)            # energy 1: the jump of the co-normal derivative (unfolded pair)
+        grad = np.zeros((3, nV))      # energy 0: grad(T1) - grad(T2), all three components
         area = 0.0
         ok = np.dot(e, e) > 0
-        for o in (p, q):
+        for sign, o in ((1.0, p), (-1.0, q)):
             # gradient of the linear interpolant over triangle (i, j, o), as a map from vertex
             # values to a 3-vector: solve the 2 edge equations in the triangle's plane
             E = np.stack([W[j] - W[i], W[o] - W[i]])               # 2x3
@@ -308,14 +309,20 @@ def _dense_least_squares(mesh: Mesh, xform, infos, ao, weight):
             row[j] += gm[0]
             row[o] += gm[1]
             row[i] -= gm[0] + gm[1]
+            grad[:, j] += sign * G[:, 0]
+            grad[:, o] += sign * G[:, 1]
+            grad[:, i] -= sign * (G[:, 0] + G[:, 1])
             area += 0.5 * np.linalg.norm(e) * h
-        if ok:
-            R += area * area * np.outer(row, row)                   # decision #6: (A1+A2)^2 J^T J
+        if ok and energy == 1:
+            R += area * area * np.outer(row, row)                   # round-1 option: (A1+A2)^2 J^T J
+        elif ok:
+            R += area * (grad.T @ grad)                             # decision #6: (A1+A2) |grad T1 - grad T2|^2
     return np.linalg.solve(M + weight * R, b), R
 
 
+@pytest.mark.parametrize("energy", [0, 1])
 @pytest.mark.parametrize("weight", [0.0, 0.1, 3.0])
-def test_least_squares_filter_against_dense_direct_solve(weight):
+def test_least_squares_filter_against_dense_direct_solve(weight, energy):
     m = scenes.heightfield(7, seed=9, height=0.4)
     xf = np.eye(4, dtype=f32)
     xf[:3, :3] = np.array([[1.3, 0.0, 0.2], [0.0, 0.9, 0.0], [-0.1, 0.0, 1.1]], dtype=f32)
@@ -325,13 +332,13 @@ def test_least_squares_filter_against_dense_direct_solve(weight):
     sb = orc.sample_instances(per, 0)
     rng = np.random.default_rng(5)
     ao = rng.uniform(0.1, 1.0, sb.n).astype(f32)
-    want, R = _dense_least_squares(m, xf, sb.infos, ao, weight)
-    got = orc.filter_least_squares(sb, ao, weight=weight, tol=1e-13)[0]
+    want, R = _dense_least_squares(m, xf, sb.infos, ao, weight, energy)
+    got = orc.filter_least_squares(sb, ao, weight=weight, tol=1e-13, energy=energy)[0]
     assert np.abs(got - want).max() < 2e-6
     # the regulariser annihilates fields that are linear in world space on a planar mesh
     if weight:
         flat = scenes.heightfield(7, seed=9, height=0.0)
-        _, Rf = _dense_least_squares(flat, xf, sb.infos[:0], ao[:0], weight)
+        _, Rf = _dense_least_squares(flat, xf, sb.infos[:0], ao[:0], weight, energy)
         Wf = flat.vertices.astype(np.float64) @ xf[:3, :3].T.astype(np.float64)
         lin = 0.3 + Wf @ np.array([0.2, -0.7, 0.05])
         assert np.abs(Rf @ lin).max() < 1e-6 * np.abs(Rf).max()    # world positions are rounded to fp32
