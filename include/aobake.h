@@ -121,8 +121,9 @@ typedef struct AoBakeParams {
                                      rays outside its range are traced by a second small launch in fp32), 1 = fp32 only */
   int32_t deferred_capacity;      /* entries of the deferred-ray list (0 = auto: 1/128 of a launch's rays); an overflow makes
                                      aobake_compute_ao repeat the launch with the fp32 kernels — settable so that tests can force it */
-  int32_t tri_batch;              /* fused kernel: lanes of a warp that must hold leaf hits before the warp runs its triangle
-                                     block (paused lanes take no node steps meanwhile); 1 = test at once, 0 = default */
+  int32_t tri_batch;              /* fused kernel: low byte = lanes of a warp that must hold leaf hits before the warp runs its
+                                     triangle block (paused lanes take no node steps meanwhile; 1 = test at once); next byte =
+                                     the most iterations a paused lane waits (0 = no limit); 0 = default (8 lanes, 6 iterations) */
   int32_t no_oversized_split;     /* BVH build: 0 = primitives (or TLAS instances) spanning more than a quarter of the scene (a ground
                                      plane under a fine mesh) are kept out of the tree and hang off one extra root node; 1 = build
                                      one tree over everything (A/B switch; both give the same hits) */
@@ -179,6 +180,10 @@ int aobake_synchronize(AoBake* ctx);
  * instance transform returns AOBAKE_ERR_INVALID_ARGUMENT and leaves the context without a
  * scene.  Only the affine 3x4 part of xform is used (the fourth row is ignored). */
 int aobake_set_scene(AoBake* ctx, const AoScene* scene, const AoScene* blockers);
+/* Uploads the scene WITHOUT building a BVH: all that bake::distributeSamples, bake::sampleInstances and
+ * bake::mapAOToVertices need (the one-shot bake:: shims of bake_api.hpp use it).  aobake_compute_ao and
+ * aobake_trace_rays then return AOBAKE_ERR_STATE. */
+int aobake_set_scene_geometry(AoBake* ctx, const AoScene* scene);
 
 /* bake::distributeSamples.  per_instance has scene->num_instances entries. */
 int aobake_distribute_samples(AoBake* ctx, size_t min_samples_per_triangle, size_t requested_num_samples,

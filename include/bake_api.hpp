@@ -83,7 +83,7 @@ inline void destroy_ao_samples(AOSamples& s) {
 inline size_t distributeSamples(const Scene& scene, size_t min_samples_per_triangle, size_t requested_num_samples,
                                 size_t* num_samples_per_instance) {
   Context c;
-  c.check(aobake_set_scene(c.get(), &scene, nullptr));
+  c.check(aobake_set_scene_geometry(c.get(), &scene));   // no ray is traced here: no BVH
   size_t total = 0;
   c.check(aobake_distribute_samples(c.get(), min_samples_per_triangle, requested_num_samples, num_samples_per_instance, &total));
   return total;
@@ -91,7 +91,7 @@ inline size_t distributeSamples(const Scene& scene, size_t min_samples_per_trian
 inline void sampleInstances(const Scene& scene, const size_t* num_samples_per_instance, size_t min_samples_per_triangle,
                             AOSamples& ao_samples) {
   Context c;
-  c.check(aobake_set_scene(c.get(), &scene, nullptr));
+  c.check(aobake_set_scene_geometry(c.get(), &scene));
   c.check(aobake_sample_instances(c.get(), num_samples_per_instance, min_samples_per_triangle, &ao_samples));
 }
 // bake_ao_optix_prime.cpp
@@ -106,7 +106,7 @@ inline void computeAO(const Scene& scene, const Scene& blockers, const AOSamples
 inline void mapAOToVertices(const Scene& scene, const size_t* num_samples_per_instance, const AOSamples& ao_samples,
                             const float* ao_values, VertexFilterMode mode, float regularization_weight, float** vertex_ao) {
   Context c;
-  c.check(aobake_set_scene(c.get(), &scene, nullptr));
+  c.check(aobake_set_scene_geometry(c.get(), &scene));
   c.check(aobake_set_samples(c.get(), &ao_samples, num_samples_per_instance));
   c.check(aobake_set_ao(c.get(), ao_values));
   c.check(aobake_map_ao_to_vertices(c.get(), (int)mode, regularization_weight, vertex_ao));

@@ -30,7 +30,7 @@ EXPORTS = [
     "aobake_synchronize", "aobake_set_scene", "aobake_distribute_samples", "aobake_sample_instances",
     "aobake_set_samples", "aobake_compute_ao", "aobake_compute_ao_range", "aobake_compute_ao_interleaved", "aobake_comm_unique_id",
     "aobake_comm_init", "aobake_comm_destroy", "aobake_compute_ao_distributed", "aobake_map_ao_to_vertices_distributed",
-    "aobake_set_scene_distributed", "aobake_set_samples_distributed", "aobake_get_ao_device", "aobake_set_ao",
+    "aobake_set_scene_distributed", "aobake_set_samples_distributed", "aobake_set_scene_geometry", "aobake_get_ao_device", "aobake_set_ao",
     "aobake_map_ao_to_vertices", "aobake_make_ground_plane", "aobake_trace_rays", "aobake_dump_rays",
     "aobake_get_hit_counts", "aobake_get_timings", "aobake_get_stats", "aobake_num_samples",
 ]
@@ -82,6 +82,8 @@ def load_library(path: Optional[str] = None):
     L.aobake_set_stream.argtypes = [vp, vp]
     L.aobake_synchronize.argtypes = [vp]
     L.aobake_set_scene.argtypes = [vp, vp, vp]
+    if hasattr(L, "aobake_set_scene_geometry"):
+        L.aobake_set_scene_geometry.argtypes = [vp, vp]
     if hasattr(L, "aobake_set_scene_distributed"):   # (absent only from older builds loaded through AOBAKE_LIB for A/B timing)
         L.aobake_set_scene_distributed.argtypes = [vp, vp, vp]
         L.aobake_set_samples_distributed.argtypes = [vp, vp, vp]
@@ -181,6 +183,13 @@ class Baker:
         pb = PackedScene(blockers) if blockers is not None and len(blockers.instances) else None
         fn = self.lib.aobake_set_scene_distributed if distributed else self.lib.aobake_set_scene
         self._ck(fn(self._h, ps.ref(), pb.ref() if pb else None))
+        self.scene = scene
+        self.per_instance = None
+
+    def set_scene_geometry(self, scene: Scene):
+        """Scene upload without a BVH: for sampling and the vertex maps only."""
+        ps = PackedScene(scene)
+        self._ck(self.lib.aobake_set_scene_geometry(self._h, ps.ref()))
         self.scene = scene
         self.per_instance = None
 
@@ -317,13 +326,13 @@ class Baker:
 # ---- one-shot forms with the reference's names and argument order (bake_api.h) ------------
 def distributeSamples(scene: Scene, min_samples_per_triangle: int, requested_num_samples: int, device: int = 0):
     with Baker(device) as b:
-        b.set_scene(scene)
+        b.set_scene_geometry(scene)
         return b.distribute_samples(min_samples_per_triangle, requested_num_samples)
 
 
 def sampleInstances(scene: Scene, num_samples_per_instance, min_samples_per_triangle: int, device: int = 0) -> SampleBuffers:
     with Baker(device) as b:
-        b.set_scene(scene)
+        b.set_scene_geometry(scene)
         return b.sample_instances(num_samples_per_instance, min_samples_per_triangle)
 
 
@@ -339,7 +348,7 @@ def computeAO(scene: Scene, blockers: Optional[Scene], ao_samples: SampleBuffers
 def mapAOToVertices(scene: Scene, num_samples_per_instance, ao_samples: SampleBuffers, ao_values: np.ndarray,
                     mode: int = FILTER_LEAST_SQUARES, regularization_weight: float = 0.1, device: int = 0):
     with Baker(device) as b:
-        b.set_scene(scene)
+        b.set_scene_geometry(scene)
         b.set_samples(ao_samples, num_samples_per_instance)
         b.set_ao(ao_values)
         return b.map_ao_to_vertices(mode, regularization_weight)

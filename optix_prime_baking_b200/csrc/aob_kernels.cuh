@@ -630,6 +630,9 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
   G.x = 0; G.y = 0;
   T.x = 0; T.y = 0;
   bool paused = false;   // the lane holds leaf hits (T) and waits for the warp's next triangle block
+  uint32_t waited = 0;   // warp-uniform: iterations since the first of the currently paused lanes paused
+  const uint32_t tri_wait = tri_batch >> 8;   // (packed by the host: low byte = lanes, next byte = iterations)
+  tri_batch &= 0xffu;
   int sp = 0;
   uint32_t c_nodes = 0, c_tris = 0, c_insts = 0;
   // Multi-GPU interleave: this launch owns the super-blocks sb (of sb_blocks 32-sample blocks) with
@@ -730,6 +733,7 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
     // instructions on configs 3 and 4, profiles/r2/srcprof_base_*.txt); batched it runs every few
     // iterations for `tri_batch` lanes.  Any-hit semantics are untouched: a paused ray does no
     // speculative work and resumes (or ends) with the result of its own test.
+    uint32_t act = __ballot_sync(0xffffffffu, ray_active);
     while (true) {
       bool hit = false;
       if (ray_active && !paused) {
@@ -780,12 +784,18 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
         }
       }
       const uint32_t pm = __ballot_sync(0xffffffffu, paused);
-      if (pm != 0u && ((uint32_t)__popc(pm) >= tri_batch || pm == __ballot_sync(0xffffffffu, ray_active))) {
-        if (paused) {
-          uint32_t tested = 0;
-          hit = test_tri_group(bvh.tris, T.x, T.y, r.org, r.dir, 0.0f, maxdist, &tested);
-          if (STATS) c_tris += tested;
-          paused = false;
+      if (pm != 0u) {
+        // run the block when enough lanes wait, when the oldest has waited tri_wait iterations (rare leaf hits must
+        // not idle a lane for longer than a ray lives), or when no lane can take a node step any more
+        waited++;
+        if ((uint32_t)__popc(pm) >= tri_batch || waited >= tri_wait || pm == act) {
+          waited = 0;
+          if (paused) {
+            uint32_t tested = 0;
+            hit = test_tri_group(bvh.tris, T.x, T.y, r.org, r.dir, 0.0f, maxdist, &tested);
+            if (STATS) c_tris += tested;
+            paused = false;
+          }
         }
       }
       // Ray end and restart are written once, straight-line: lanes ending on a hit, lanes ending
@@ -812,9 +822,9 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
           if (la_valid) start_queued();
         }
       }
-      const uint32_t act2 = __ballot_sync(0xffffffffu, ray_active);
-      if (act2 == 0u) break;
-      if ((uint32_t)__popc(act2) < refill_below) {
+      act = __ballot_sync(0xffffffffu, ray_active);   // (unchanged until the end of the next iteration: reused by the pause test)
+      if (act == 0u) break;
+      if ((uint32_t)__popc(act) < refill_below) {
         // leave only if some idle lane can actually take a new ray
         const bool can = !ray_active && ((have_item && pass < pass_end) || !exhausted);  // (a queued ray would already have started)
         if (__any_sync(0xffffffffu, can)) break;
@@ -1149,6 +1159,90 @@ __global__ void k_ls_dir(double* __restrict__ S, double* __restrict__ bank, doub
       __threadfence();
     }
   }
+}
+// ---- row-partitioned PCG across ranks (one big system, e.g. the single 10 M-vertex instance of config 5) ----
+// Rank r owns the vertex rows [v0, v1).  It walks only the triangles / edges that touch one of its rows
+// (flagged once, compacted into item lists) and adds only into its own rows, so the product needs no
+// reduction across ranks; what it needs from the others is p at the vertices its items reference — the
+// BOUNDARY vertices (those sharing an item with a vertex of another owner), exchanged once per iteration.
+__global__ void k_ls_flag_items(const uint32_t* __restrict__ gtris, uint64_t NT, const LsEdge* __restrict__ edges, uint64_t NE, uint32_t v0, uint32_t v1,
+                                uint32_t rows_per_rank, uint8_t* __restrict__ tri_mine, uint8_t* __restrict__ edge_mine, uint8_t* __restrict__ boundary) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  auto mine = [&](uint32_t v) { return v >= v0 && v < v1; };
+  if (i < NT) {
+    const uint32_t a = gtris[3 * i], b = gtris[3 * i + 1], c = gtris[3 * i + 2];
+    tri_mine[i] = (mine(a) || mine(b) || mine(c)) ? 1 : 0;
+    const uint32_t oa = a / rows_per_rank, ob = b / rows_per_rank, oc = c / rows_per_rank;
+    if (oa != ob || oa != oc) { boundary[a] = 1; boundary[b] = 1; boundary[c] = 1; }
+  }
+  if (i < NE) {
+    const LsEdge E = edges[i];
+    const bool live = E.W != 0.0;
+    edge_mine[i] = (live && (mine(E.i) || mine(E.j) || mine(E.p) || mine(E.q))) ? 1 : 0;
+    const uint32_t o = E.i / rows_per_rank;
+    if (live && (E.j / rows_per_rank != o || E.p / rows_per_rank != o || E.q / rows_per_rank != o)) {
+      boundary[E.i] = 1; boundary[E.j] = 1; boundary[E.p] = 1; boundary[E.q] = 1;
+    }
+  }
+}
+// y[rows v0..v1) += (M + w R) x over this rank's item lists
+__global__ void k_ls_apply_rows(const uint32_t* __restrict__ tri_list, uint32_t n_tri, const uint32_t* __restrict__ edge_list, uint32_t n_edge,
+                                const uint32_t* __restrict__ tris, const double* __restrict__ Mt, const LsEdge* __restrict__ edges, double w,
+                                uint32_t v0, uint32_t v1, const double* __restrict__ x, double* __restrict__ y) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  auto add = [&](uint32_t v, double val) { if (v >= v0 && v < v1) atomicAdd(&y[v], val); };
+  if (k < n_tri) {
+    const uint64_t i = tri_list[k];
+    const uint32_t a = tris[3 * i], b = tris[3 * i + 1], c = tris[3 * i + 2];
+    const double* M = Mt + 6 * i;
+    const double m0 = M[0], m1 = M[1], m2 = M[2], m3 = M[3], m4 = M[4], m5 = M[5];
+    if (m0 != 0.0 || m3 != 0.0 || m5 != 0.0) {
+      const double x0 = x[a], x1 = x[b], x2 = x[c];
+      add(a, m0 * x0 + m1 * x1 + m2 * x2);
+      add(b, m1 * x0 + m3 * x1 + m4 * x2);
+      add(c, m2 * x0 + m4 * x1 + m5 * x2);
+    }
+  }
+  if (k < n_edge) {
+    const LsEdge E = edges[edge_list[k]];
+    double al[3], be[3];
+    ls_edge_coeffs(E, al, be);
+    const double xi = x[E.i], xj = x[E.j];
+    const double a1 = al[0] * xi + al[1] * xj + al[2] * x[E.p], a2 = be[0] * xi + be[1] * xj + be[2] * x[E.q];
+    const double g1 = w * E.W * (a1 - E.c * a2), g2 = w * E.W * (a2 - E.c * a1);
+    add(E.i, g1 * al[0] + g2 * be[0]); add(E.j, g1 * al[1] + g2 * be[1]);
+    add(E.p, g1 * al[2]); add(E.q, g2 * be[2]);
+  }
+}
+__global__ void k_iota_u32(uint32_t* __restrict__ a, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = (uint32_t)i;
+}
+// first index k with list[k] >= bound[s], for every s (list sorted ascending)
+__global__ void k_lower_bounds(const uint32_t* __restrict__ list, uint32_t n, const uint32_t* __restrict__ bound, uint32_t n_bounds, uint32_t* __restrict__ out) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_bounds) return;
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (list[mid] < bound[s]) lo = mid + 1; else hi = mid;
+  }
+  out[s] = lo;
+}
+__global__ void k_gather_d(const double* __restrict__ src, const uint32_t* __restrict__ idx, uint32_t begin, uint32_t end, double* __restrict__ buf) {
+  const uint32_t k = begin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < end) buf[k] = src[idx[k]];
+}
+// dst[idx[k]] = buf[k] for k outside [skip_begin, skip_end) (the caller's own segment)
+__global__ void k_scatter_d(double* __restrict__ dst, const uint32_t* __restrict__ idx, uint32_t n, uint32_t skip_begin, uint32_t skip_end,
+                            const double* __restrict__ buf) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n && (k < skip_begin || k >= skip_end)) dst[idx[k]] = buf[k];
+}
+// out[v] = (float)x[v] for rows [v0, v1), 0 elsewhere (a sum all-reduce then assembles the vector)
+__global__ void k_d2f_rows(const double* __restrict__ x, float* __restrict__ out, uint64_t n, uint32_t v0, uint32_t v1) {
+  const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < n) out[v] = (v >= v0 && v < v1) ? (float)x[v] : 0.0f;
 }
 __global__ void k_d2f(const double* __restrict__ x, float* __restrict__ out, uint64_t n) {
   const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

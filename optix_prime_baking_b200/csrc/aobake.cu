@@ -78,7 +78,7 @@ struct NcclApi {
   }
 };
 NcclApi g_nccl;
-constexpr int kNcclFloat = 7, kNcclInt32 = 2, kNcclUint8 = 1, kNcclSum = 0, kNcclMax = 2;   // ncclFloat32, ncclInt32, ncclUint8; ncclSum, ncclMax
+constexpr int kNcclFloat = 7, kNcclDouble = 8, kNcclInt32 = 2, kNcclUint8 = 1, kNcclSum = 0, kNcclMax = 2;   // ncclFloat32/64, ncclInt32, ncclUint8; ncclSum, ncclMax
 
 template <typename T>
 struct DBuf {
@@ -159,6 +159,7 @@ struct AoBake {
 
   // scene
   bool have_scene = false;
+  bool have_bvh = false;                   // false after aobake_set_scene_geometry: nothing to trace against
   std::vector<DeviceMesh> meshes;          // scene meshes (blockers are only needed for the BVH)
   std::vector<HostInstance> insts;         // scene instances
   std::vector<uint64_t> inst_num_verts;
@@ -222,7 +223,7 @@ struct AoBake {
 namespace {
 
 constexpr uint32_t kDefaultBlockSamples = 65536;   // super-block of the interleaved multi-GPU partition
-constexpr uint32_t kTriBatchFlat = 6, kTriBatchTwoLevel = 6;   // default AoBakeParams::tri_batch (sweep: profiles/r2/sweep_tri_batch.log)
+constexpr uint32_t kTriBatchFlat = 8 | (6 << 8), kTriBatchTwoLevel = 8 | (6 << 8);   // default AoBakeParams::tri_batch (sweep: profiles/r2/sweep_tri_batch.log)
 
 // Makes a local status collective: every rank of the communicator calls this once at the same point
 // with its own status; all of them return non-zero if any rank failed, so that no rank enters the
@@ -586,7 +587,7 @@ int aobake_synchronize(AoBake* ctx) {
   return AOBAKE_OK;
 }
 
-static int set_scene_impl(AoBake* ctx, const AoScene* scene, const AoScene* blockers, bool shard) {
+static int set_scene_impl(AoBake* ctx, const AoScene* scene, const AoScene* blockers, bool shard, bool build_bvh = true) {
   if (!ctx || !scene) return AOBAKE_ERR_INVALID_ARGUMENT;
   if (shard && ctx->comm_size > 1 && !ctx->nccl_comm) return ctx->fail(AOBAKE_ERR_STATE, "aobake_comm_init has not been called");
   shard = shard && ctx->comm_size > 1;
@@ -597,6 +598,7 @@ static int set_scene_impl(AoBake* ctx, const AoScene* scene, const AoScene* bloc
   int rc;
   if ((rc = check_scene(ctx, scene, "scene")) || (rc = check_scene(ctx, blockers, "blockers"))) return rc;
   ctx->have_scene = false;
+  ctx->have_bvh = false;
   ctx->areas_ready = false;
   ctx->num_samples = 0;
   ctx->have_ao = false;
@@ -659,6 +661,15 @@ static int set_scene_impl(AoBake* ctx, const AoScene* scene, const AoScene* bloc
                        m < ctx->meshes.size() ? m : m - ctx->meshes.size());
   CK(cudaEventElapsedTime(&ctx->timings.upload_ms, ctx->ev0, ctx->ev1));
 
+  if (!build_bvh) {
+    // geometry only (aobake_set_scene_geometry): enough for distribute/sample_instances and the vertex maps
+    ctx->d_nodes.release(); ctx->d_tris.release(); ctx->d_insts.release();
+    memset(&ctx->stats, 0, sizeof(ctx->stats));
+    ctx->timings.bvh_build_ms = 0.f;
+    ctx->have_bvh = false;
+    ctx->have_scene = true;
+    return AOBAKE_OK;
+  }
   // ---- instancing mode (decision #12) ----
   bool two_level = ctx->params.instancing_mode == AOBAKE_INSTANCING_TWO_LEVEL;
   if (ctx->params.instancing_mode == AOBAKE_INSTANCING_AUTO) {
@@ -865,6 +876,7 @@ static int set_scene_impl(AoBake* ctx, const AoScene* scene, const AoScene* bloc
   CK(cudaStreamSynchronize(st));
   CK(cudaEventElapsedTime(&ctx->timings.bvh_build_ms, ctx->ev0, ctx->ev1));
   ctx->have_scene = true;
+  ctx->have_bvh = true;
   return AOBAKE_OK;
 }
 
@@ -873,6 +885,8 @@ int aobake_set_scene(AoBake* ctx, const AoScene* scene, const AoScene* blockers)
 int aobake_set_scene_distributed(AoBake* ctx, const AoScene* scene, const AoScene* blockers) {
   return set_scene_impl(ctx, scene, blockers, true);
 }
+
+int aobake_set_scene_geometry(AoBake* ctx, const AoScene* scene) { return set_scene_impl(ctx, scene, nullptr, false, false); }
 
 int aobake_distribute_samples(AoBake* ctx, size_t min_per_tri, size_t requested, size_t* per_instance, size_t* total) {
   if (!ctx || !per_instance) return AOBAKE_ERR_INVALID_ARGUMENT;
@@ -1041,7 +1055,7 @@ size_t aobake_num_samples(const AoBake* ctx) { return ctx ? ctx->num_samples : 0
 static int compute_ao_impl(AoBake* ctx, size_t begin, size_t end, int rays_per_sample, float offset, float maxdist, float* host_ao,
                            uint32_t part, uint32_t num_parts, uint32_t block_samples, bool force_fp32 = false) {
   if (!ctx) return AOBAKE_ERR_INVALID_ARGUMENT;
-  if (!ctx->have_scene) return ctx->fail(AOBAKE_ERR_STATE, "compute_ao before set_scene");
+  if (!ctx->have_scene || !ctx->have_bvh) return ctx->fail(AOBAKE_ERR_STATE, "compute_ao before set_scene (aobake_set_scene_geometry builds no BVH)");
   if (begin > end || end > ctx->num_samples) return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "sample range [%zu,%zu) outside [0,%llu)", begin, end, (unsigned long long)ctx->num_samples);
   if (rays_per_sample < 1) return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "rays_per_sample must be >= 1");
   if (ctx->samples_sharded && !(num_parts == (uint32_t)ctx->comm_size && part == (uint32_t)ctx->comm_rank && begin == 0 && end == ctx->num_samples &&
@@ -1148,7 +1162,12 @@ static int compute_ao_impl(AoBake* ctx, size_t begin, size_t end, int rays_per_s
     }
     const uint32_t refill = ctx->params.refill_below > 0 ? (uint32_t)ctx->params.refill_below : 28u;
     // lanes that must hold leaf hits before the warp runs its triangle block (1 = test at once)
-    const uint32_t tri_batch = ctx->params.tri_batch > 0 ? (uint32_t)std::min(ctx->params.tri_batch, 32) : (ctx->two_level ? kTriBatchTwoLevel : kTriBatchFlat);
+    // tri_batch = lanes | iterations << 8 (the longest a paused lane waits); iterations 0 => no limit
+    uint32_t tri_batch = ctx->params.tri_batch > 0 ? (uint32_t)ctx->params.tri_batch : (ctx->two_level ? kTriBatchTwoLevel : kTriBatchFlat);
+    {
+      const uint32_t lanes = std::min(std::max(tri_batch & 0xffu, 1u), 32u), wait = (tri_batch >> 8) & 0xffu;
+      tri_batch = lanes | ((wait ? wait : 255u) << 8);
+    }
     kern<<<grid, kAoBlock, 0, st>>>(bvh, S, (uint64_t)begin, (uint32_t)n, q, offset, maxdist, n_chunks, refill, tri_batch, part, num_parts, sb_blocks,
                                     (uint32_t)n_local_blocks, ctx->d_hits.p + begin, ctx->d_counter.p, ctx->d_stats.p, deferred);
     CKL();
@@ -1336,7 +1355,10 @@ int area_filter_batched(AoBake* ctx, uint32_t ib, uint32_t ie, DBuf<float>& d_ou
 
 // bake_filter_least_squares.cpp: (M + w R) x = b, fp64, for ALL instances as one block-diagonal
 // system, matrix-free Jacobi-PCG.
-int ls_filter_batched(AoBake* ctx, float weight, uint32_t ib, uint32_t ie, DBuf<float>& d_out) {
+// rows = true (multi-GPU, fewer instances than ranks): every rank assembles the whole system [ib, ie) = all instances
+// and the PCG is partitioned by vertex ROWS across the ranks of the communicator (see k_ls_flag_items); d_out then
+// holds this rank's rows and zeros elsewhere.
+int ls_filter_batched(AoBake* ctx, float weight, uint32_t ib, uint32_t ie, DBuf<float>& d_out, bool rows = false) {
   cudaStream_t st = ctx->stream;
   const uint32_t nI = ie - ib;
   const double w = weight;
@@ -1399,16 +1421,85 @@ int ls_filter_batched(AoBake* ctx, float weight, uint32_t ib, uint32_t ie, DBuf<
   CKL();
   // scal: [0] = |b|^2, [1] = r.z of the previous iteration, [2] = |r|^2 and [3] = p.Ap of the last finished iteration,
   // [4..6] and [8..10] = the two accumulator banks {p.Ap, r.z, |r|^2} (iteration parity)
-  const unsigned vec_grid = std::min<unsigned>(grid_for(v1, 256), (unsigned)ctx->sm_count * 8u);
-  const uint64_t nwork = std::max<uint64_t>(NT, NE);
+  const int nranks = rows ? ctx->comm_size : 1;
+  const uint32_t rows_per_rank = (uint32_t)((NV + (uint64_t)nranks - 1) / (uint64_t)nranks);
+  const uint32_t r0 = rows ? (uint32_t)std::min<uint64_t>((uint64_t)ctx->comm_rank * rows_per_rank, NV) : 0u;
+  const uint32_t r1 = rows ? (uint32_t)std::min<uint64_t>((uint64_t)r0 + rows_per_rank, NV) : (uint32_t)NV;
+  const uint64_t n_rows = r1 - r0;
+  // ---- row partition: this rank's item lists and the boundary vertices all ranks exchange ----
+  DBuf<uint32_t> tri_list, edge_list, bidx, d_boff;
+  DBuf<double> hbuf;
+  uint32_t n_tri_mine = 0, n_edge_mine = 0, n_boundary = 0;
+  std::vector<uint32_t> boff(nranks + 1, 0);
+  if (rows) {
+    DBuf<uint8_t> tri_mine, edge_mine, boundary;
+    DBuf<uint32_t> counts, d_bound;
+    CK(tri_mine.alloc(t1)); CK(edge_mine.alloc(std::max<uint64_t>(NE, 1))); CK(boundary.alloc(v1)); CK(counts.alloc(3));
+    CK(tri_list.alloc(t1)); CK(edge_list.alloc(std::max<uint64_t>(NE, 1))); CK(bidx.alloc(v1)); CK(d_boff.alloc(nranks + 1)); CK(d_bound.alloc(nranks + 1));
+    CK(cudaMemsetAsync(boundary.p, 0, v1, st));
+    const uint64_t nitems = std::max<uint64_t>(NT, NE);
+    if (nitems) k_ls_flag_items<<<grid_for(nitems, 256), 256, 0, st>>>(gtris.p, NT, edges.p, NE, r0, r1, std::max(rows_per_rank, 1u), tri_mine.p, edge_mine.p, boundary.p);
+    CKL();
+    auto select = [&](const uint8_t* flags, uint64_t n, uint32_t* out, uint32_t* d_count) -> int {
+      if (!n) return AOBAKE_OK;
+      cub::CountingInputIterator<uint32_t> iota(0u);
+      size_t tmp_bytes = 0;
+      CK(cub::DeviceSelect::Flagged(nullptr, tmp_bytes, iota, flags, out, d_count, (long long)n, st));
+      DBuf<uint8_t> tmp;
+      CK(tmp.alloc(tmp_bytes));
+      CK(cub::DeviceSelect::Flagged(tmp.p, tmp_bytes, iota, flags, out, d_count, (long long)n, st));
+      return AOBAKE_OK;
+    };
+    CK(cudaMemsetAsync(counts.p, 0, 3 * sizeof(uint32_t), st));
+    int rc;
+    if ((rc = select(tri_mine.p, NT, tri_list.p, counts.p)) || (rc = select(edge_mine.p, NE, edge_list.p, counts.p + 1)) ||
+        (rc = select(boundary.p, NV, bidx.p, counts.p + 2)))
+      return rc;
+    uint32_t hc[3];
+    CK(cudaMemcpyAsync(hc, counts.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    n_tri_mine = hc[0]; n_edge_mine = hc[1]; n_boundary = hc[2];
+    std::vector<uint32_t> bound(nranks + 1);
+    for (int s2 = 0; s2 <= nranks; s2++) bound[s2] = (uint32_t)std::min<uint64_t>((uint64_t)s2 * rows_per_rank, NV);
+    CK(cudaMemcpyAsync(d_bound.p, bound.data(), (nranks + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    k_lower_bounds<<<1, 64, 0, st>>>(bidx.p, n_boundary, d_bound.p, (uint32_t)(nranks + 1), d_boff.p);
+    CKL();
+    CK(cudaMemcpyAsync(boff.data(), d_boff.p, (nranks + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(hbuf.alloc(std::max(n_boundary, 1u)));
+  }
+  // a scalar every rank needs the same value of: summed over the ranks (the result of an all-reduce is identical on
+  // all of them, so they take the same number of iterations and stay in step)
+  auto all_sum = [&](double* d, size_t count) -> int {
+    if (!rows) return AOBAKE_OK;
+    const int nrc = g_nccl.AllReduce(d, d, count, kNcclDouble, kNcclSum, ctx->nccl_comm, st);
+    return nrc == 0 ? AOBAKE_OK : ctx->fail(AOBAKE_ERR_COMM, "ncclAllReduce: %s", g_nccl.GetErrorString(nrc));
+  };
+  // p at the boundary vertices: every owner broadcasts its segment of the (sorted) boundary list
+  auto exchange_boundary = [&]() -> int {
+    if (!rows || !n_boundary) return AOBAKE_OK;
+    const uint32_t mb = boff[ctx->comm_rank], me = boff[ctx->comm_rank + 1];
+    if (me > mb) k_gather_d<<<grid_for(me - mb, 256), 256, 0, st>>>(p.p, bidx.p, mb, me, hbuf.p);
+    int nrc = g_nccl.GroupStart();
+    for (int s2 = 0; s2 < nranks && nrc == 0; s2++)
+      if (boff[s2 + 1] > boff[s2]) nrc = g_nccl.Broadcast(hbuf.p + boff[s2], hbuf.p + boff[s2], boff[s2 + 1] - boff[s2], kNcclDouble, s2, ctx->nccl_comm, st);
+    const int nrc2 = g_nccl.GroupEnd();
+    if (nrc != 0 || nrc2 != 0) return ctx->fail(AOBAKE_ERR_COMM, "ncclBroadcast (boundary exchange): %s", g_nccl.GetErrorString(nrc ? nrc : nrc2));
+    k_scatter_d<<<grid_for(n_boundary, 256), 256, 0, st>>>(p.p, bidx.p, n_boundary, mb, me, hbuf.p);
+    return AOBAKE_OK;
+  };
+  const unsigned vec_grid = std::min<unsigned>(grid_for(std::max<uint64_t>(n_rows, 1), 256), (unsigned)ctx->sm_count * 8u);
+  const uint64_t nwork = rows ? std::max<uint64_t>(n_tri_mine, n_edge_mine) : std::max<uint64_t>(NT, NE);
   DBuf<unsigned int> done_blocks;
   CK(done_blocks.alloc(1));
   CK(cudaMemsetAsync(done_blocks.p, 0, sizeof(unsigned int), st));
   CK(cudaMemsetAsync(scal.p, 0, 12 * sizeof(double), st));
-  if (NV) {
-    k_dot<<<vec_grid, 256, 0, st>>>(rhs.p, rhs.p, NV, scal.p + 0);
-    k_dot<<<vec_grid, 256, 0, st>>>(r.p, z.p, NV, scal.p + 1);
+  int rc;
+  if (n_rows) {
+    k_dot<<<vec_grid, 256, 0, st>>>(rhs.p + r0, rhs.p + r0, n_rows, scal.p + 0);
+    k_dot<<<vec_grid, 256, 0, st>>>(r.p + r0, z.p + r0, n_rows, scal.p + 1);
   }
+  if ((rc = all_sum(scal.p, 2))) return rc;
   double hs[4];
   CK(cudaMemcpyAsync(hs, scal.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
@@ -1424,10 +1515,16 @@ int ls_filter_batched(AoBake* ctx, float weight, uint32_t ib, uint32_t ie, DBuf<
       for (int k = 0; k < burst; k++, it++) {
         double* bank = scal.p + 4 + 4 * (it & 1);
         double* other = scal.p + 4 + 4 * ((it + 1) & 1);
-        if (nwork) k_ls_apply<<<grid_for(nwork, 256), 256, 0, st>>>(gtris.p, NT, Mt.p, edges.p, (uint32_t)NE, w, p.p, Ap.p);
-        k_ls_pap<<<vec_grid, 256, 0, st>>>(fixed.p, p.p, Ap.p, NV, bank);
-        k_ls_update<<<vec_grid, 256, 0, st>>>(scal.p, p.p, Ap.p, diag.p, x.p, r.p, z.p, NV, bank);
-        k_ls_dir<<<vec_grid, 256, 0, st>>>(scal.p, bank, other, z.p, p.p, Ap.p, NV, done_blocks.p);
+        if (nwork) {
+          if (rows) k_ls_apply_rows<<<grid_for(nwork, 256), 256, 0, st>>>(tri_list.p, n_tri_mine, edge_list.p, n_edge_mine, gtris.p, Mt.p, edges.p, w, r0, r1, p.p, Ap.p);
+          else k_ls_apply<<<grid_for(nwork, 256), 256, 0, st>>>(gtris.p, NT, Mt.p, edges.p, (uint32_t)NE, w, p.p, Ap.p);
+        }
+        k_ls_pap<<<vec_grid, 256, 0, st>>>(fixed.p + r0, p.p + r0, Ap.p + r0, n_rows, bank);
+        if ((rc = all_sum(bank, 1))) return rc;
+        k_ls_update<<<vec_grid, 256, 0, st>>>(scal.p, p.p + r0, Ap.p + r0, diag.p + r0, x.p + r0, r.p + r0, z.p + r0, n_rows, bank);
+        if ((rc = all_sum(bank + 1, 2))) return rc;
+        k_ls_dir<<<vec_grid, 256, 0, st>>>(scal.p, bank, other, z.p + r0, p.p + r0, Ap.p + r0, n_rows, done_blocks.p);
+        if ((rc = exchange_boundary())) return rc;
       }
       CKL();
       CK(cudaMemcpyAsync(hs, scal.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
@@ -1440,7 +1537,10 @@ int ls_filter_batched(AoBake* ctx, float weight, uint32_t ib, uint32_t ie, DBuf<
     CK(cudaMemsetAsync(x.p, 0, NV * sizeof(double), st));
   }
   ctx->timings.cg_iterations = it;
-  if (NV) k_d2f<<<grid_for(NV, 256), 256, 0, st>>>(x.p, d_out.p, NV);
+  if (NV) {
+    if (rows) k_d2f_rows<<<grid_for(NV, 256), 256, 0, st>>>(x.p, d_out.p, NV, r0, r1);
+    else k_d2f<<<grid_for(NV, 256), 256, 0, st>>>(x.p, d_out.p, NV);
+  }
   CKL();
   CK(cudaStreamSynchronize(st));
   return AOBAKE_OK;
@@ -1479,8 +1579,11 @@ static int map_ao_impl(AoBake* ctx, int mode, float weight, float* const* host_v
     ie = ctx->comm_rank + 1 == ctx->comm_size ? nI : std::min(cut(ctx->comm_rank + 1), nI);
     if (ie < ib) ie = ib;
   }
+  // fewer instances than ranks (the single big mesh of configs 3/5): one system, its rows split over the ranks
+  const bool rows = dist && mode == AOBAKE_FILTER_LEAST_SQUARES && nI < (uint32_t)ctx->comm_size && NVall > 0;
+  if (rows) { ib = 0; ie = nI; }
   DBuf<float> d_sub;
-  int rc = mode == AOBAKE_FILTER_LEAST_SQUARES ? ls_filter_batched(ctx, weight, ib, ie, d_sub) : area_filter_batched(ctx, ib, ie, d_sub);
+  int rc = mode == AOBAKE_FILTER_LEAST_SQUARES ? ls_filter_batched(ctx, weight, ib, ie, d_sub, rows) : area_filter_batched(ctx, ib, ie, d_sub);
   if (dist) rc = comm_agree(ctx, rc);   // e.g. a CG breakdown on one rank must not strand the others in the all-reduce
   if (rc) return rc;
   const float* d_all = d_sub.p;   // vertex AO of every instance, global numbering
@@ -1538,7 +1641,7 @@ int aobake_make_ground_plane(const float bbox_min[3], const float bbox_max[3], i
 
 int aobake_trace_rays(AoBake* ctx, const float* rays, size_t n, uint8_t* hit) {
   if (!ctx || (n && (!rays || !hit))) return AOBAKE_ERR_INVALID_ARGUMENT;
-  if (!ctx->have_scene) return ctx->fail(AOBAKE_ERR_STATE, "trace_rays before set_scene");
+  if (!ctx->have_scene || !ctx->have_bvh) return ctx->fail(AOBAKE_ERR_STATE, "trace_rays before set_scene (aobake_set_scene_geometry builds no BVH)");
   ScopedTimer tm(ctx);
   CK(cudaSetDevice(ctx->device));
   if (!n) return AOBAKE_OK;

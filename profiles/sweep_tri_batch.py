@@ -8,7 +8,12 @@ import bench  # noqa: E402
 from optix_prime_baking_b200 import api, scenes  # noqa: E402
 
 w = sys.argv[1]
-vals = [int(x) for x in (sys.argv[2] if len(sys.argv) > 2 else "1,2,4,6,8,12,16").split(",")]
+def parse(x):   # "lanes" or "lanes:iterations"
+    a = x.split(":")
+    return int(a[0]) | ((int(a[1]) if len(a) > 1 else 0) << 8)
+
+
+vals = [parse(x) for x in (sys.argv[2] if len(sys.argv) > 2 else "1,2,4,6,8,12,16").split(",")]
 scene, blockers, min_per, requested, desc = bench.make_workload(w)
 rays = bench.RAYS[w]
 off, maxd = scenes.default_distances(scene)
@@ -27,4 +32,4 @@ for tb in vals:
         h = int(bk.hit_counts()[b:b + n].astype("int64").sum())
         ref = h if ref is None else ref
         q2 = bench.sqrt_rays(rays) ** 2
-        print(f"{w} tri_batch {tb:2d}  {min(ts):9.2f} ms  {n * q2 / min(ts) / 1e6:6.2f} Grays/s  hits {'same' if h == ref else 'DIFFERENT'}", flush=True)
+        print(f"{w} tri_batch {tb & 255:2d} lanes / {tb >> 8:2d} iterations  {min(ts):9.2f} ms  {n * q2 / min(ts) / 1e6:6.2f} Grays/s  hits {'same' if h == ref else 'DIFFERENT'}", flush=True)

@@ -534,3 +534,27 @@ def test_many_large_triangles_stay_in_the_tree(api):
         got = bk.trace_rays(rays)
     want = orc.trace_rays(rays, brute=True)
     check_hits(orc, rays, got, want)
+
+
+def test_geometry_only_scene_serves_sampling_and_vertex_maps(api):
+    """aobake_set_scene_geometry (what the one-shot bake::distributeSamples / sampleInstances / mapAOToVertices
+    shims use): no BVH is built, sampling and the vertex maps match a full context, tracing is a state error."""
+    scene, blockers = SCENES["sphere_ground"]
+    off, maxd = scenes.default_distances(scene)
+    with api.Baker() as full, api.Baker() as geo:
+        full.set_scene(scene, blockers)
+        geo.set_scene_geometry(scene)
+        assert geo.stats().num_bvh_nodes == 0
+        ta, pa = full.distribute_samples(2, 0)
+        tb, pb = geo.distribute_samples(2, 0)
+        assert ta == tb and np.array_equal(pa, pb)
+        sa = full.sample_instances(pa, 2)
+        assert_samples_equal(sa, geo.sample_instances(pb, 2))
+        ao = full.compute_ao(64, off, maxd)
+        with pytest.raises(api.AoBakeError) as e:
+            geo.compute_ao(64, off, maxd)
+        assert e.value.code == 3      # AOBAKE_ERR_STATE
+        geo.set_ao(ao)
+        for mode in (api.FILTER_AREA_BASED, api.FILTER_LEAST_SQUARES):
+            va, vb = full.map_ao_to_vertices(mode, 0.1)[0], geo.map_ao_to_vertices(mode, 0.1)[0]
+            assert np.abs(va - vb).max() < 1e-5
