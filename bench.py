@@ -6,7 +6,7 @@
 Workload (default): BASELINE.json configs[2] — the 20M-triangle procedural mesh, a FIXED budget of
 10 M area-weighted sample points, 1024 rays/sample = 10.24 G rays per step — at every N.  The job is
 the same at N = 1, 2, 4, 8 ("scaling": "strong"): the BVH is replicated, the samples are sharded over
-the ranks in interleaved super-blocks of 65536, and the exchange (one in-place ncclAllReduce over the
+the ranks in interleaved super-blocks of 16384, and the exchange (one in-place ncclAllReduce over the
 resident ao[] array, issued by libaobake.so's own communicator) is INSIDE the timed region.
 
 A "step" is one pass of the hot path (bake::computeAO's ray generation + any-hit traversal +
@@ -42,7 +42,7 @@ if ROOT not in sys.path:
 from optix_prime_baking_b200 import scenes  # noqa: E402
 
 RAYS = {"c1": 64, "c2": 256, "c3": 1024, "c4": 256, "c5": 1024}
-BLOCK_SAMPLES = 65536
+BLOCK_SAMPLES = 16384
 PROFILE_ROUND = "r2"
 
 

@@ -123,7 +123,7 @@ typedef struct AoBakeParams {
                                      aobake_compute_ao repeat the launch with the fp32 kernels — settable so that tests can force it */
   int32_t tri_batch;              /* fused kernel: low byte = lanes of a warp that must hold leaf hits before the warp runs its
                                      triangle block (paused lanes take no node steps meanwhile; 1 = test at once); next byte =
-                                     the most iterations a paused lane waits (0 = no limit); 0 = default (8 lanes, 6 iterations) */
+                                     the most iterations a paused lane waits (0 = no limit); 0 = default (8 lanes flattened, 12 under a TLAS; 6 iterations) */
   int32_t no_oversized_split;     /* BVH build: 0 = primitives (or TLAS instances) spanning more than a quarter of the scene (a ground
                                      plane under a fine mesh) are kept out of the tree and hang off one extra root node; 1 = build
                                      one tree over everything (A/B switch; both give the same hits) */
@@ -208,7 +208,7 @@ int aobake_compute_ao(AoBake* ctx, int rays_per_sample, float scene_offset, floa
 int aobake_compute_ao_range(AoBake* ctx, size_t begin, size_t end, int rays_per_sample, float scene_offset,
                             float scene_maxdistance, float* host_ao);
 /* Interleaved multi-GPU partition of the whole sample set: this call traces the super-blocks of
- * block_samples samples (multiple of 32; 0 => 65536) whose index % num_parts == part, and sets the
+ * block_samples samples (multiple of 32; 0 => 16384) whose index % num_parts == part, and sets the
  * resident ao[] of every other sample to 0 — a sum all-reduce over the parts then assembles the
  * full array exactly.  Interleaving evens out regions of different traversal cost (the contiguous
  * ranges of aobake_compute_ao_range can differ by 10-15 % on a terrain). */
@@ -230,7 +230,7 @@ int aobake_compute_ao_distributed(AoBake* ctx, int rays_per_sample, float scene_
  * host arrays (what bake::computeAO receives on every rank).  set_scene_distributed: rank r copies only
  * slice r of every vertex / index array over its own PCIe link and one in-place ncclAllGather per
  * array completes them over NVLink (N uploads of the whole scene become one); every rank then builds
- * the same BVH.  set_samples_distributed: only the super-blocks of 65536 samples this rank traces in
+ * the same BVH.  set_samples_distributed: only the super-blocks of 16384 samples this rank traces in
  * aobake_compute_ao_distributed are copied (positions / normals / face normals; sample_infos whole,
  * the vertex maps need them); afterwards only aobake_compute_ao_distributed may trace.  With one
  * rank both are the plain calls.  A rank that fails before a collective makes every rank return

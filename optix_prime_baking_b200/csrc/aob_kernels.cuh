@@ -753,35 +753,9 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
           T = G;  // a postponed TLAS primitive group
           G.x = 0; G.y = 0;
         }
-        if (T.y) {
-          if (in_blas) {
-            paused = true;
-          } else if (TWO_LEVEL) {
-            // instances of the group: skip those whose bounding sphere the world ray cannot touch,
-            // enter the first one it can — save the TLAS continuation, switch to object space
-            while (T.y) {
-              const int b = __ffs((int)T.y) - 1;
-              T.y &= T.y - 1u;
-              const F4* rec = bvh.insts + (uint64_t)kInstF4 * ((uint64_t)T.x + (uint32_t)b);
-              if (!sphere_may_hit(org, wdir, ld_f4(rec + 4))) continue;
-              if (T.y) push(sp, T);
-              if (G.y & 0xff000000u) push(sp, G);
-              U2 sen;
-              sen.x = kSentinel; sen.y = 0;
-              push(sp, sen);
-              const F4 r0 = ld_f4(rec), r1 = ld_f4(rec + 1), r2 = ld_f4(rec + 2), r3 = ld_f4(rec + 3);
-              const float m[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
-              if (STATS) c_insts++;
-              r.org = xf_point(m, org);
-              r.dir = xf_vector(m, wdir);
-              r.idir = v3(safe_rcp(r.dir.x), safe_rcp(r.dir.y), safe_rcp(r.dir.z));
-              in_blas = true;
-              G.x = __float_as_uint(r3.x);
-              G.y = (1u << 24) | 1u;
-              break;
-            }
-          }
-        }
+        // leaf hits (triangles inside a BLAS / a flattened scene, instances in a TLAS) are not processed at once: the
+        // lane pauses and the warp handles them in one block (below)
+        if (T.y) paused = true;
       }
       const uint32_t pm = __ballot_sync(0xffffffffu, paused);
       if (pm != 0u) {
@@ -791,10 +765,36 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
         if ((uint32_t)__popc(pm) >= tri_batch || waited >= tri_wait || pm == act) {
           waited = 0;
           if (paused) {
-            uint32_t tested = 0;
-            hit = test_tri_group(bvh.tris, T.x, T.y, r.org, r.dir, 0.0f, maxdist, &tested);
-            if (STATS) c_tris += tested;
             paused = false;
+            if (in_blas) {
+              uint32_t tested = 0;
+              hit = test_tri_group(bvh.tris, T.x, T.y, r.org, r.dir, 0.0f, maxdist, &tested);
+              if (STATS) c_tris += tested;
+            } else if (TWO_LEVEL) {
+              // instances of the group: skip those whose bounding sphere the world ray cannot touch,
+              // enter the first one it can — save the TLAS continuation, switch to object space
+              while (T.y) {
+                const int b = __ffs((int)T.y) - 1;
+                T.y &= T.y - 1u;
+                const F4* rec = bvh.insts + (uint64_t)kInstF4 * ((uint64_t)T.x + (uint32_t)b);
+                if (!sphere_may_hit(org, wdir, ld_f4(rec + 4))) continue;
+                if (T.y) push(sp, T);
+                if (G.y & 0xff000000u) push(sp, G);
+                U2 sen;
+                sen.x = kSentinel; sen.y = 0;
+                push(sp, sen);
+                const F4 r0 = ld_f4(rec), r1 = ld_f4(rec + 1), r2 = ld_f4(rec + 2), r3 = ld_f4(rec + 3);
+                const float m[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
+                if (STATS) c_insts++;
+                r.org = xf_point(m, org);
+                r.dir = xf_vector(m, wdir);
+                r.idir = v3(safe_rcp(r.dir.x), safe_rcp(r.dir.y), safe_rcp(r.dir.z));
+                in_blas = true;
+                G.x = __float_as_uint(r3.x);
+                G.y = (1u << 24) | 1u;
+                break;
+              }
+            }
           }
         }
       }

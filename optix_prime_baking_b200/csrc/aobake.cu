@@ -222,8 +222,12 @@ struct AoBake {
 
 namespace {
 
-constexpr uint32_t kDefaultBlockSamples = 65536;   // super-block of the interleaved multi-GPU partition
-constexpr uint32_t kTriBatchFlat = 8 | (6 << 8), kTriBatchTwoLevel = 8 | (6 << 8);   // default AoBakeParams::tri_batch (sweep: profiles/r2/sweep_tri_batch.log)
+constexpr uint32_t kDefaultBlockSamples = 16384;   // super-block of the interleaved multi-GPU partition (config 3 at 8 ranks: 76 or 77 per rank)
+#ifndef AOB_ITEMS_PER_WARP
+#define AOB_ITEMS_PER_WARP 32
+#endif
+constexpr uint32_t kItemsPerWarp = AOB_ITEMS_PER_WARP;
+constexpr uint32_t kTriBatchFlat = 8 | (6 << 8), kTriBatchTwoLevel = 12 | (6 << 8);   // default AoBakeParams::tri_batch (sweep: profiles/r2/sweep_tri_batch.log)
 
 // Makes a local status collective: every rank of the communicator calls this once at the same point
 // with its own status; all of them return non-zero if any rank failed, so that no rank enters the
@@ -1143,8 +1147,10 @@ static int compute_ao_impl(AoBake* ctx, size_t begin, size_t end, int rays_per_s
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kAoBlock, 0));
     if (per_sm < 1) per_sm = 1;
     const uint64_t resident_threads = (uint64_t)per_sm * ctx->sm_count * kAoBlock;
+    // work items (32-sample block x strata chunk) per resident warp: below ~32 the last items of the launch leave most
+    // warps idle (a rank's share of config 3 at 8 GPUs is 9 blocks per warp: 13 % tail) — split the strata
     uint32_t n_chunks = 1;
-    while (owned_samples * n_chunks < 8 * resident_threads && n_chunks * 2 <= q2) n_chunks *= 2;
+    while (owned_samples * n_chunks < (uint64_t)kItemsPerWarp * resident_threads && n_chunks * 2 <= q2) n_chunks *= 2;
     unsigned grid = (unsigned)(per_sm * ctx->sm_count);
     const uint64_t items = std::max<uint64_t>(owned_samples, 1) * n_chunks;
     if ((uint64_t)grid * kAoBlock > items) grid = (unsigned)((items + kAoBlock - 1) / kAoBlock);

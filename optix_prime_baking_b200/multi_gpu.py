@@ -17,7 +17,7 @@ def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
     return (rank * total) // world, ((rank + 1) * total) // world
 
 
-def owned_mask(total: int, part: int, num_parts: int, block_samples: int = 65536) -> np.ndarray:
+def owned_mask(total: int, part: int, num_parts: int, block_samples: int = 16384) -> np.ndarray:
     """Samples traced by `part` under the interleaved partition (aobake_compute_ao_interleaved):
     super-blocks of block_samples samples, dealt round-robin."""
     return (np.arange(total, dtype=np.int64) // block_samples) % num_parts == part
@@ -57,7 +57,7 @@ class DistributedBaker:
         self.bk, self.rank, self.world, self.device, self.group = baker, rank, world, device, group
 
     def compute_ao(self, rays_per_sample: int, scene_offset: float, scene_maxdistance: float, gather: bool = True,
-                   download: bool = False, interleave: bool = True, block_samples: int = 65536) -> Optional[np.ndarray]:
+                   download: bool = False, interleave: bool = True, block_samples: int = 16384) -> Optional[np.ndarray]:
         """interleave=True (default): rank r traces the 64k-sample super-blocks with index % R == r
         (even load on scenes whose regions differ in traversal cost) and the resident ao[] arrays
         are summed in place with one all-reduce — every other rank contributes exact zeros, so the
