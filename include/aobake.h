@@ -130,7 +130,8 @@ typedef struct AoBakeParams {
   int32_t ls_energy;              /* least-squares regulariser per interior edge: 0 = (A1 + A2) |grad(T1) - grad(T2)|^2, the 3-D
                                      gradient jump of Kavan et al. 2011; 1 = (A1 + A2)^2 x (jump of the co-normal
                                      derivative)^2, the scale-free variant of round 1 (same null space, far better conditioned) */
-  int32_t reserved[1];
+  int32_t ls_matrix_free;         /* least-squares PCG product: 0 = A = M + wR assembled once (sliced ELL, no atomics per iteration;
+                                     rows of vertices with too many neighbours stay matrix-free), 1 = matrix-free scatter */
 } AoBakeParams;
 
 typedef struct AoTimings {        /* milliseconds, device-timed with CUDA events unless noted */
@@ -157,7 +158,9 @@ typedef struct AoStats {
   uint64_t rays;
   int32_t two_level;
   int32_t reserved[7];            /* [0] = depth of the top-level 8-wide tree, [1] = deepest BLAS (two-level),
-                                     [2] = rays the last compute_ao handed to the deferred fp32 launch */
+                                     [2] = rays the last compute_ao handed to the deferred fp32 launch,
+                                     [3] = 1 if the last least-squares solve used the assembled matrix,
+                                     [4] = rows of that solve multiplied matrix-free (more columns than the assembly holds) */
 } AoStats;
 
 typedef struct AoBake AoBake;

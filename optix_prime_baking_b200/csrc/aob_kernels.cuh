@@ -1160,6 +1160,153 @@ __global__ void k_ls_dir(double* __restrict__ S, double* __restrict__ bank, doub
     }
   }
 }
+// ---- explicit matrix for the PCG product (round 2) --------------------------------------------------------------
+// The matrix-free product above scatters 4 fp64 atomics per edge and 3 per triangle (180 M atomics per iteration on
+// config 5) and re-reads every 64-byte edge record: ~1.07 ms per iteration for 10 M unknowns.  The few thousand
+// iterations the faithful regulariser needs (decision 6) make it worth assembling A = M + wR once:
+//   1. every owned row gets a small open-addressing hash table (kLsHashCap columns); triangles add their 3 x 3 mass
+//      block, edges their 4 x 4 block w W [(al al^T + be be^T) - c (al be^T + be al^T)], anchored rows +1 on the
+//      diagonal — fp64 atomics once, not once per iteration;
+//   2. the tables are compacted into sliced ELL (slices of 32 rows, padded to the slice's longest row, column-major
+//      inside a slice: coalesced loads, ~14 entries per row on a triangle mesh);
+//   3. the product is one thread per row, no atomics, deterministic, with the anchored rows and the p.Ap partial
+//      sums folded in.
+// A row with more distinct columns than the table holds (a vertex of valence > ~14: the pole of a UV sphere, the hub
+// of a fan) is flagged; flagged rows are left empty in the matrix and multiplied matrix-free from the (few) triangles
+// and edges that touch them (k_ls_flag_over_items, k_ls_apply_rows with a row mask, k_ls_pap_list).
+constexpr uint32_t kLsHashCap = 32;
+constexpr uint32_t kLsEmpty = 0xffffffffu;
+AOB_D void ls_hash_add(uint32_t* __restrict__ keys, double* __restrict__ vals, uint64_t row_rel, uint32_t col, double v, uint8_t* __restrict__ row_over) {
+  uint32_t* k = keys + row_rel * kLsHashCap;
+  double* d = vals + row_rel * kLsHashCap;
+  uint32_t s = (col * 2654435761u) >> 27;   // top 5 bits
+  for (uint32_t probe = 0; probe < kLsHashCap; probe++, s = (s + 1u) & (kLsHashCap - 1u)) {
+    const uint32_t old = atomicCAS(&k[s], kLsEmpty, col);
+    if (old == kLsEmpty || old == col) { atomicAdd(&d[s], v); return; }
+  }
+  row_over[row_rel] = 1;   // more distinct columns than the table holds: this ROW is multiplied matrix-free
+}
+// one thread per listed (or every) triangle / edge: rows outside [v0, v1) are skipped
+__global__ void k_ls_assemble(const uint32_t* __restrict__ tri_list, uint64_t n_tri, const uint32_t* __restrict__ edge_list, uint64_t n_edge,
+                              const uint32_t* __restrict__ tris, const double* __restrict__ Mt, const LsEdge* __restrict__ edges, double w,
+                              uint32_t v0, uint32_t v1, uint32_t* __restrict__ keys, double* __restrict__ vals, uint8_t* __restrict__ row_over) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  auto add = [&](uint32_t r, uint32_t c, double v) { if (r >= v0 && r < v1 && v != 0.0) ls_hash_add(keys, vals, r - v0, c, v, row_over); };
+  if (k < n_tri) {
+    const uint64_t i = tri_list ? tri_list[k] : k;
+    const double* M = Mt + 6 * i;
+    const double m[6] = {M[0], M[1], M[2], M[3], M[4], M[5]};
+    if (m[0] != 0.0 || m[3] != 0.0 || m[5] != 0.0) {
+      const uint32_t a = tris[3 * i], b = tris[3 * i + 1], c = tris[3 * i + 2];
+      add(a, a, m[0]); add(a, b, m[1]); add(a, c, m[2]);
+      add(b, a, m[1]); add(b, b, m[3]); add(b, c, m[4]);
+      add(c, a, m[2]); add(c, b, m[4]); add(c, c, m[5]);
+    }
+  }
+  if (k < n_edge) {
+    const LsEdge E = edges[edge_list ? edge_list[k] : k];
+    if (E.W != 0.0) {
+      double al3[3], be3[3];
+      ls_edge_coeffs(E, al3, be3);
+      const uint32_t v[4] = {E.i, E.j, E.p, E.q};
+      const double al[4] = {al3[0], al3[1], al3[2], 0.0}, be[4] = {be3[0], be3[1], 0.0, be3[2]};
+      const double ww = w * E.W;
+#pragma unroll
+      for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) add(v[r], v[c], ww * (al[r] * al[c] + be[r] * be[c] - E.c * (al[r] * be[c] + be[r] * al[c])));
+    }
+  }
+}
+// anchored rows (decision #7) carry +1 on the diagonal; every row gets its diagonal slot so that no row is empty
+__global__ void k_ls_assemble_diag(const uint8_t* __restrict__ fixed, uint32_t v0, uint32_t v1, uint32_t* __restrict__ keys, double* __restrict__ vals,
+                                   uint8_t* __restrict__ row_over) {
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < v1 - v0) ls_hash_add(keys, vals, r, v0 + (uint32_t)r, fixed[v0 + r] ? 1.0 : 0.0, row_over);
+}
+// items that touch a flagged row (row_over is indexed by v - v0 for v in [v0, v1))
+__global__ void k_ls_flag_over_items(const uint32_t* __restrict__ tri_list, uint64_t n_tri, const uint32_t* __restrict__ edge_list, uint64_t n_edge,
+                                     const uint32_t* __restrict__ tris, const LsEdge* __restrict__ edges, uint32_t v0, uint32_t v1,
+                                     const uint8_t* __restrict__ row_over, uint8_t* __restrict__ tri_flag, uint8_t* __restrict__ edge_flag) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  auto over = [&](uint32_t v) { return v >= v0 && v < v1 && row_over[v - v0] != 0; };
+  if (k < n_tri) {
+    const uint64_t i = tri_list ? tri_list[k] : k;
+    tri_flag[k] = (over(tris[3 * i]) || over(tris[3 * i + 1]) || over(tris[3 * i + 2])) ? 1 : 0;
+  }
+  if (k < n_edge) {
+    const LsEdge E = edges[edge_list ? edge_list[k] : k];
+    edge_flag[k] = (E.W != 0.0 && (over(E.i) || over(E.j) || over(E.p) || over(E.q))) ? 1 : 0;
+  }
+}
+// out[k] = list ? list[sel[k]] : sel[k]   (positions selected in a list -> the item ids themselves)
+__global__ void k_compose_u32(const uint32_t* __restrict__ list, const uint32_t* __restrict__ sel, uint32_t n, uint32_t* __restrict__ out) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) out[k] = list ? list[sel[k]] : sel[k];
+}
+// flagged rows: anchored-row term and their share of p.Ap (one block)
+__global__ void k_ls_pap_list(const uint32_t* __restrict__ rows_rel, uint32_t n, uint32_t v0, const uint8_t* __restrict__ fixed, const double* __restrict__ p,
+                              double* __restrict__ Ap, double* __restrict__ bank) {
+  __shared__ double sh[32];
+  double acc = 0.0;
+  for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
+    const uint32_t v = v0 + rows_rel[k];
+    double a = Ap[v];
+    if (fixed[v]) { a += p[v]; Ap[v] = a; }
+    acc += p[v] * a;
+  }
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) atomicAdd(&bank[0], acc);
+}
+__global__ void k_u32_to_u64(const uint32_t* __restrict__ a, uint64_t n, uint64_t* __restrict__ out) {   // out[n] = 0 (scan sentinel)
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= n) out[i] = i < n ? a[i] : 0ull;
+}
+// entries per row and, per slice of 32 rows, the padded width
+__global__ void k_ls_row_widths(const uint32_t* __restrict__ keys, const uint8_t* __restrict__ row_over, uint64_t n_rows, uint32_t* __restrict__ row_nnz,
+                                uint32_t* __restrict__ slice_width) {
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t n = 0;
+  if (r < n_rows && !row_over[r])
+    for (uint32_t s = 0; s < kLsHashCap; s++) n += keys[r * kLsHashCap + s] != kLsEmpty ? 1u : 0u;
+  if (r < n_rows) row_nnz[r] = n;
+  uint32_t m = n;
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && r < n_rows) slice_width[r >> 5] = m;
+}
+// sliced ELL: entry k of row r sits at slice_off[r / 32] * 32 + k * 32 + r % 32; padding = (column r, value 0)
+__global__ void k_ls_fill_sell(const uint32_t* __restrict__ keys, const double* __restrict__ vals, const uint8_t* __restrict__ row_over, uint64_t n_rows, uint32_t v0,
+                               const uint64_t* __restrict__ slice_off, const uint32_t* __restrict__ slice_width, uint32_t* __restrict__ cols,
+                               double* __restrict__ A) {
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  const uint64_t base = slice_off[r >> 5] * 32ull + (r & 31);
+  const uint32_t width = slice_width[r >> 5];
+  uint32_t k = 0;
+  for (uint32_t s = 0; s < kLsHashCap && !row_over[r]; s++) {
+    const uint32_t c = keys[r * kLsHashCap + s];
+    if (c != kLsEmpty) { cols[base + 32ull * k] = c; A[base + 32ull * k] = vals[r * kLsHashCap + s]; k++; }
+  }
+  for (; k < width; k++) { cols[base + 32ull * k] = v0 + (uint32_t)r; A[base + 32ull * k] = 0.0; }
+}
+// Ap[v0 + r] = (A p)[row r]; bank[0] += p.Ap over these rows.  256-thread blocks (8 slices).
+__global__ void k_ls_spmv_sell(const uint64_t* __restrict__ slice_off, const uint32_t* __restrict__ slice_width, const uint32_t* __restrict__ cols,
+                               const double* __restrict__ A, uint64_t n_rows, uint32_t v0, const double* __restrict__ p, double* __restrict__ Ap,
+                               double* __restrict__ bank) {
+  __shared__ double sh[32];
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double acc = 0.0, y = 0.0;
+  if (r < n_rows) {
+    const uint64_t base = slice_off[r >> 5] * 32ull + (r & 31);
+    const uint32_t width = slice_width[r >> 5];
+    for (uint32_t k = 0; k < width; k++) y += A[base + 32ull * k] * __ldg(&p[cols[base + 32ull * k]]);
+    Ap[v0 + r] = y;
+    acc = p[v0 + r] * y;
+  }
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) atomicAdd(&bank[0], acc);
+}
+
 // ---- row-partitioned PCG across ranks (one big system, e.g. the single 10 M-vertex instance of config 5) ----
 // Rank r owns the vertex rows [v0, v1).  It walks only the triangles / edges that touch one of its rows
 // (flagged once, compacted into item lists) and adds only into its own rows, so the product needs no
@@ -1188,9 +1335,10 @@ __global__ void k_ls_flag_items(const uint32_t* __restrict__ gtris, uint64_t NT,
 // y[rows v0..v1) += (M + w R) x over this rank's item lists
 __global__ void k_ls_apply_rows(const uint32_t* __restrict__ tri_list, uint32_t n_tri, const uint32_t* __restrict__ edge_list, uint32_t n_edge,
                                 const uint32_t* __restrict__ tris, const double* __restrict__ Mt, const LsEdge* __restrict__ edges, double w,
-                                uint32_t v0, uint32_t v1, const double* __restrict__ x, double* __restrict__ y) {
+                                uint32_t v0, uint32_t v1, const uint8_t* __restrict__ row_mask /*nullable: only rows with row_mask[v - v0]*/,
+                                const double* __restrict__ x, double* __restrict__ y) {
   const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  auto add = [&](uint32_t v, double val) { if (v >= v0 && v < v1) atomicAdd(&y[v], val); };
+  auto add = [&](uint32_t v, double val) { if (v >= v0 && v < v1 && (!row_mask || row_mask[v - v0])) atomicAdd(&y[v], val); };
   if (k < n_tri) {
     const uint64_t i = tri_list[k];
     const uint32_t a = tris[3 * i], b = tris[3 * i + 1], c = tris[3 * i + 2];

@@ -514,6 +514,7 @@ int aobake_default_params(AoBakeParams* p) {
   p->tri_batch = 0;
   p->no_oversized_split = 0;
   p->ls_energy = 0;
+  p->ls_matrix_free = 0;
   return AOBAKE_OK;
 }
 
@@ -1494,6 +1495,88 @@ int ls_filter_batched(AoBake* ctx, float weight, uint32_t ib, uint32_t ie, DBuf<
     k_scatter_d<<<grid_for(n_boundary, 256), 256, 0, st>>>(p.p, bidx.p, n_boundary, mb, me, hbuf.p);
     return AOBAKE_OK;
   };
+  // ---- A = M + wR assembled once into sliced ELL (k_ls_assemble ... k_ls_spmv_sell); the matrix-free product stays as
+  // the fallback for rows with more columns than the assembly tables hold, and as the A/B switch ls_matrix_free ----
+  bool use_matrix = ctx->params.ls_matrix_free == 0 && n_rows > 0;
+  DBuf<uint32_t> sell_cols, slice_width, over_rows, over_tris, over_edges;
+  DBuf<uint64_t> slice_off;
+  DBuf<double> sell_vals;
+  DBuf<uint8_t> row_over;
+  uint32_t n_over_rows = 0, n_over_tris = 0, n_over_edges = 0;
+  if (use_matrix) {
+    const uint64_t n_slices = (n_rows + 31) / 32;
+    DBuf<uint32_t> hkeys, row_nnz;
+    DBuf<double> hvals;
+    DBuf<uint64_t> width64;
+    CK(hkeys.alloc(n_rows * kLsHashCap)); CK(hvals.alloc(n_rows * kLsHashCap)); CK(row_nnz.alloc(n_rows)); CK(row_over.alloc(n_rows));
+    CK(slice_width.alloc(n_slices)); CK(slice_off.alloc(n_slices + 1)); CK(width64.alloc(n_slices + 1));
+    CK(cudaMemsetAsync(hkeys.p, 0xff, n_rows * kLsHashCap * sizeof(uint32_t), st));
+    CK(cudaMemsetAsync(hvals.p, 0, n_rows * kLsHashCap * sizeof(double), st));
+    CK(cudaMemsetAsync(row_over.p, 0, n_rows, st));
+    const uint64_t a_tri = rows ? n_tri_mine : NT, a_edge = rows ? n_edge_mine : NE;
+    const uint32_t* a_tri_list = rows ? tri_list.p : nullptr;
+    const uint32_t* a_edge_list = rows ? edge_list.p : nullptr;
+    if (std::max(a_tri, a_edge))
+      k_ls_assemble<<<grid_for(std::max(a_tri, a_edge), 256), 256, 0, st>>>(a_tri_list, a_tri, a_edge_list, a_edge, gtris.p, Mt.p, edges.p, w, r0, r1, hkeys.p,
+                                                                           hvals.p, row_over.p);
+    k_ls_assemble_diag<<<grid_for(n_rows, 256), 256, 0, st>>>(fixed.p, r0, r1, hkeys.p, hvals.p, row_over.p);
+    k_ls_row_widths<<<grid_for(n_slices * 32, 256), 256, 0, st>>>(hkeys.p, row_over.p, n_rows, row_nnz.p, slice_width.p);
+    k_u32_to_u64<<<grid_for(n_slices + 1, 256), 256, 0, st>>>(slice_width.p, n_slices, width64.p);
+    CKL();
+    {
+      size_t tmp_bytes = 0;
+      CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, width64.p, slice_off.p, (long long)(n_slices + 1), st));
+      DBuf<uint8_t> tmp;
+      CK(tmp.alloc(tmp_bytes));
+      CK(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, width64.p, slice_off.p, (long long)(n_slices + 1), st));
+    }
+    // rows whose table overflowed, and the items that touch them (multiplied matrix-free every iteration)
+    auto select_u8 = [&](const uint8_t* flags, uint64_t n, uint32_t* out, uint32_t* d_count) -> int {
+      cub::CountingInputIterator<uint32_t> iota(0u);
+      size_t tmp_bytes = 0;
+      CK(cub::DeviceSelect::Flagged(nullptr, tmp_bytes, iota, flags, out, d_count, (long long)n, st));
+      DBuf<uint8_t> tmp;
+      CK(tmp.alloc(tmp_bytes));
+      CK(cub::DeviceSelect::Flagged(tmp.p, tmp_bytes, iota, flags, out, d_count, (long long)n, st));
+      return AOBAKE_OK;
+    };
+    DBuf<uint32_t> d_cnt;
+    CK(d_cnt.alloc(3));
+    CK(cudaMemsetAsync(d_cnt.p, 0, 3 * sizeof(uint32_t), st));
+    CK(over_rows.alloc(n_rows));
+    int rc2;
+    if ((rc2 = select_u8(row_over.p, n_rows, over_rows.p, d_cnt.p))) return rc2;
+    uint32_t h_cnt[3] = {0, 0, 0};
+    uint64_t total_width = 0;
+    CK(cudaMemcpyAsync(h_cnt, d_cnt.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&total_width, slice_off.p + n_slices, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    n_over_rows = h_cnt[0];
+    if (n_over_rows) {
+      DBuf<uint8_t> tflag, eflag;
+      DBuf<uint32_t> tsel, esel;
+      CK(tflag.alloc(std::max<uint64_t>(a_tri, 1))); CK(eflag.alloc(std::max<uint64_t>(a_edge, 1)));
+      CK(tsel.alloc(std::max<uint64_t>(a_tri, 1))); CK(esel.alloc(std::max<uint64_t>(a_edge, 1)));
+      k_ls_flag_over_items<<<grid_for(std::max<uint64_t>(std::max(a_tri, a_edge), 1), 256), 256, 0, st>>>(a_tri_list, a_tri, a_edge_list, a_edge, gtris.p, edges.p, r0,
+                                                                                                    r1, row_over.p, tflag.p, eflag.p);
+      CKL();
+      if (a_tri && (rc2 = select_u8(tflag.p, a_tri, tsel.p, d_cnt.p + 1))) return rc2;
+      if (a_edge && (rc2 = select_u8(eflag.p, a_edge, esel.p, d_cnt.p + 2))) return rc2;
+      CK(cudaMemcpyAsync(h_cnt, d_cnt.p, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      n_over_tris = h_cnt[1]; n_over_edges = h_cnt[2];
+      CK(over_tris.alloc(std::max(n_over_tris, 1u))); CK(over_edges.alloc(std::max(n_over_edges, 1u)));
+      if (n_over_tris) k_compose_u32<<<grid_for(n_over_tris, 256), 256, 0, st>>>(a_tri_list, tsel.p, n_over_tris, over_tris.p);
+      if (n_over_edges) k_compose_u32<<<grid_for(n_over_edges, 256), 256, 0, st>>>(a_edge_list, esel.p, n_over_edges, over_edges.p);
+      CKL();
+    }
+    CK(sell_cols.alloc(std::max<uint64_t>(total_width * 32, 1))); CK(sell_vals.alloc(std::max<uint64_t>(total_width * 32, 1)));
+    k_ls_fill_sell<<<grid_for(n_rows, 256), 256, 0, st>>>(hkeys.p, hvals.p, row_over.p, n_rows, r0, slice_off.p, slice_width.p, sell_cols.p, sell_vals.p);
+    CKL();
+    CK(cudaStreamSynchronize(st));   // the tables are released here
+  }
+  ctx->stats.reserved[3] = use_matrix ? 1 : 0;
+  ctx->stats.reserved[4] = (int32_t)n_over_rows;
   const unsigned vec_grid = std::min<unsigned>(grid_for(std::max<uint64_t>(n_rows, 1), 256), (unsigned)ctx->sm_count * 8u);
   const uint64_t nwork = rows ? std::max<uint64_t>(n_tri_mine, n_edge_mine) : std::max<uint64_t>(NT, NE);
   DBuf<unsigned int> done_blocks;
@@ -1521,11 +1604,20 @@ int ls_filter_batched(AoBake* ctx, float weight, uint32_t ib, uint32_t ie, DBuf<
       for (int k = 0; k < burst; k++, it++) {
         double* bank = scal.p + 4 + 4 * (it & 1);
         double* other = scal.p + 4 + 4 * ((it + 1) & 1);
-        if (nwork) {
-          if (rows) k_ls_apply_rows<<<grid_for(nwork, 256), 256, 0, st>>>(tri_list.p, n_tri_mine, edge_list.p, n_edge_mine, gtris.p, Mt.p, edges.p, w, r0, r1, p.p, Ap.p);
-          else k_ls_apply<<<grid_for(nwork, 256), 256, 0, st>>>(gtris.p, NT, Mt.p, edges.p, (uint32_t)NE, w, p.p, Ap.p);
+        if (use_matrix) {
+          k_ls_spmv_sell<<<grid_for(n_rows, 256), 256, 0, st>>>(slice_off.p, slice_width.p, sell_cols.p, sell_vals.p, n_rows, r0, p.p, Ap.p, bank);
+          if (n_over_rows) {   // the flagged rows (empty in the matrix): matrix-free from the items that touch them
+            const uint32_t nw = std::max(n_over_tris, n_over_edges);
+            if (nw) k_ls_apply_rows<<<grid_for(nw, 256), 256, 0, st>>>(over_tris.p, n_over_tris, over_edges.p, n_over_edges, gtris.p, Mt.p, edges.p, w, r0, r1, row_over.p, p.p, Ap.p);
+            k_ls_pap_list<<<1, 256, 0, st>>>(over_rows.p, n_over_rows, r0, fixed.p, p.p, Ap.p, bank);
+          }
+        } else {
+          if (nwork) {
+            if (rows) k_ls_apply_rows<<<grid_for(nwork, 256), 256, 0, st>>>(tri_list.p, n_tri_mine, edge_list.p, n_edge_mine, gtris.p, Mt.p, edges.p, w, r0, r1, nullptr, p.p, Ap.p);
+            else k_ls_apply<<<grid_for(nwork, 256), 256, 0, st>>>(gtris.p, NT, Mt.p, edges.p, (uint32_t)NE, w, p.p, Ap.p);
+          }
+          k_ls_pap<<<vec_grid, 256, 0, st>>>(fixed.p + r0, p.p + r0, Ap.p + r0, n_rows, bank);
         }
-        k_ls_pap<<<vec_grid, 256, 0, st>>>(fixed.p + r0, p.p + r0, Ap.p + r0, n_rows, bank);
         if ((rc = all_sum(bank, 1))) return rc;
         k_ls_update<<<vec_grid, 256, 0, st>>>(scal.p, p.p + r0, Ap.p + r0, diag.p + r0, x.p + r0, r.p + r0, z.p + r0, n_rows, bank);
         if ((rc = all_sum(bank + 1, 2))) return rc;

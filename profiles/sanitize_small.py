@@ -22,5 +22,17 @@ for name, (scene, blockers) in {"sphere": scenes.config1_sphere(20, 20),
             hit = bk.trace_rays(rays.reshape(-1, 8))
             v1 = bk.map_ao_to_vertices(api.FILTER_AREA_BASED)
             v2 = bk.map_ao_to_vertices(api.FILTER_LEAST_SQUARES, 0.1)
+            # round 2: the NCCL entry points with a one-rank communicator, sharded uploads, both PCG products
+            bk.comm_init(0, 1, api.Baker.comm_unique_id())
+            bk.set_scene(scene, blockers, distributed=True)
+            bk.set_samples(sb, per, distributed=True)
+            bk.compute_ao_distributed(16, off, maxd)
+            v3 = bk.map_ao_to_vertices(api.FILTER_LEAST_SQUARES, 0.1, distributed=True)
+            bk.comm_destroy()
+        with api.Baker(trace_kernel=tk, ls_matrix_free=True, ls_energy=1, tri_batch=1, no_oversized_split=True) as bk:
+            bk.set_scene(scene, blockers)
+            bk.set_samples(sb, per)
+            bk.compute_ao(16, off, maxd, download=False)
+            v4 = bk.map_ao_to_vertices(api.FILTER_LEAST_SQUARES, 0.1)
         print(name, "kernel", tk, "samples", total, "ao mean %.4f" % ao.mean(), "hit rate %.3f" % hit.mean(), flush=True)
 print("sanitize run ok")

@@ -558,3 +558,49 @@ def test_geometry_only_scene_serves_sampling_and_vertex_maps(api):
         for mode in (api.FILTER_AREA_BASED, api.FILTER_LEAST_SQUARES):
             va, vb = full.map_ao_to_vertices(mode, 0.1)[0], geo.map_ao_to_vertices(mode, 0.1)[0]
             assert np.abs(va - vb).max() < 1e-5
+
+
+@pytest.mark.parametrize("name", ["sphere_ground", "instanced", "sheared"])
+@pytest.mark.parametrize("energy", [0, 1])
+def test_least_squares_assembled_matrix_equals_matrix_free(api, name, energy):
+    """The PCG product through the assembled sliced-ELL matrix (default) and the matrix-free scatter give the same
+    vertex AO, and both match the oracle."""
+    scene, blockers = SCENES[name]
+    off, maxd = scenes.default_distances(scene)
+    orc = Oracle(scene, blockers)
+    out = {}
+    for mf in (False, True):
+        with api.Baker(ls_matrix_free=mf, ls_energy=energy, cg_tolerance=1e-9) as bk:
+            bk.set_scene(scene, blockers)
+            total, per = bk.distribute_samples(2, 0)
+            sb = bk.sample_instances(per, 2)
+            ao = bk.compute_ao(16, off, maxd)
+            out[mf] = bk.map_ao_to_vertices(api.FILTER_LEAST_SQUARES, 0.1)
+            assert bk.stats().reserved[3] == (0 if mf else 1)
+    for a, b in zip(out[False], out[True]):
+        assert np.abs(a - b).max() < 1e-5
+    want = orc.filter_least_squares(sb, ao, 0.1, tol=1e-10, per_instance=per, energy=energy)
+    for a, b in zip(out[False], want):
+        assert np.abs(a - b).max() <= VERTEX_AO_TOL
+
+
+def test_least_squares_high_valence_rows_are_multiplied_matrix_free(api):
+    """A 48-triangle fan: the hub row has more columns than the assembly table holds; that row (and only it) is
+    multiplied matrix-free — same answer as the oracle."""
+    n = 48
+    ang = 2 * np.pi * np.arange(n) / n
+    v = np.concatenate([[[0, 0.3, 0]], np.stack([np.cos(ang), 0.05 * np.sin(3 * ang), np.sin(ang)], axis=1)]).astype(np.float32)
+    t = np.array([[0, 1 + (k + 1) % n, 1 + k] for k in range(n)], dtype=np.uint32)
+    scene = Scene([Mesh(v, t)], [Instance(0)])
+    blockers = scenes.ground_blockers(scene)
+    off, maxd = scenes.default_distances(scene)
+    orc = Oracle(scene, blockers)
+    with api.Baker(cg_tolerance=1e-9) as bk:
+        bk.set_scene(scene, blockers)
+        total, per = bk.distribute_samples(4, 0)
+        sb = bk.sample_instances(per, 4)
+        ao = bk.compute_ao(16, off, maxd)
+        got = bk.map_ao_to_vertices(api.FILTER_LEAST_SQUARES, 0.1)[0]
+        assert bk.stats().reserved[3] == 1 and bk.stats().reserved[4] == 1     # assembled matrix, one row outside it
+    want = orc.filter_least_squares(sb, ao, 0.1, tol=1e-10, per_instance=per)[0]
+    assert np.abs(got - want).max() <= VERTEX_AO_TOL
