@@ -506,13 +506,16 @@ AOB_D uint32_t expand_hit_bits(uint32_t hb, uint32_t im, uint32_t meta_lo, uint3
 // pipe): legal whenever tmax exceeds the scene diagonal, which is the AO default (10 x the scene
 // extent) — culling by tmax can then never reject a box inside the scene, and the triangle test
 // still enforces t < tmax exactly.
+// intersect_node8_raw returns the 8 slot hit bits; intersect_node8 expands them into the traversal mask.
 template <bool CLAMP_TMAX = true>
-AOB_D uint32_t intersect_node8(const U4* nodes, uint32_t idx, const RayState& r, const NodeConsts& nc, uint32_t* child_base,
-                               uint32_t* prim_base, uint32_t* imask) {
+AOB_D uint32_t intersect_node8_raw(const U4* nodes, uint32_t idx, const RayState& r, const NodeConsts& nc, uint32_t* child_base,
+                                   uint32_t* prim_base, uint32_t* imask, uint32_t* meta_lo, uint32_t* meta_hi) {
   const U4* p = nodes + 5ull * idx;
   const U4 n0 = ld_u4(p), n1 = ld_u4(p + 1), n2 = ld_u4(p + 2), n3 = ld_u4(p + 3), n4 = ld_u4(p + 4);
   *child_base = n1.x;
   *prim_base = n1.y;
+  *meta_lo = n1.z;
+  *meta_hi = n1.w;
   const uint32_t im = n0.w >> 24;
   *imask = im;
   const float adx = as_float((n0.w & 0xffu) << 23) * r.idir.x;
@@ -549,7 +552,14 @@ AOB_D uint32_t intersect_node8(const U4* nodes, uint32_t idx, const RayState& r,
     const float tf = CLAMP_TMAX ? fminf(fminf(tfx, tfy), fminf(tfz, r.tmax)) : fminf(fminf(tfx, tfy), tfz);
     miss = shift_in_sign(miss, as_uint(tf - tn));
   }
-  return expand_hit_bits(~miss & 0xffu, im, n1.z, n1.w);
+  return ~miss & 0xffu;
+}
+template <bool CLAMP_TMAX = true>
+AOB_D uint32_t intersect_node8(const U4* nodes, uint32_t idx, const RayState& r, const NodeConsts& nc, uint32_t* child_base,
+                               uint32_t* prim_base, uint32_t* imask) {
+  uint32_t mlo, mhi;
+  const uint32_t hb = intersect_node8_raw<CLAMP_TMAX>(nodes, idx, r, nc, child_base, prim_base, imask, &mlo, &mhi);
+  return expand_hit_bits(hb, *imask, mlo, mhi);
 }
 
 // The same test in packed fp16, two planes per instruction (HFMA2 / HMNMX2): the (near, far) bytes of
@@ -578,12 +588,14 @@ AOB_D uint32_t intersect_node8(const U4* nodes, uint32_t idx, const RayState& r,
 #ifndef AOB_H2_CORNER_FRAME
 #define AOB_H2_CORNER_FRAME 0
 #endif
-AOB_D uint32_t intersect_node8_h2(const U4* nodes, uint32_t idx, const RayState& r, uint32_t* child_base, uint32_t* prim_base,
-                                  uint32_t* imask) {
+AOB_D uint32_t intersect_node8_h2_raw(const U4* nodes, uint32_t idx, const RayState& r, uint32_t* child_base, uint32_t* prim_base,
+                                      uint32_t* imask, uint32_t* meta_lo, uint32_t* meta_hi) {
   const U4* p = nodes + 5ull * idx;
   const U4 n0 = ld_u4(p), n1 = ld_u4(p + 1), n2 = ld_u4(p + 2), n3 = ld_u4(p + 3), n4 = ld_u4(p + 4);
   *child_base = n1.x;
   *prim_base = n1.y;
+  *meta_lo = n1.z;
+  *meta_hi = n1.w;
   const uint32_t im = n0.w >> 24;
   *imask = im;
   const float sx = as_float((n0.w & 0xffu) << 23), sy = as_float(((n0.w >> 8) & 0xffu) << 23), sz = as_float(((n0.w >> 16) & 0xffu) << 23);
@@ -624,7 +636,28 @@ AOB_D uint32_t intersect_node8_h2(const U4* nodes, uint32_t idx, const RayState&
     const uint32_t m = h2_min(h2_min(tx, ty), h2_min(tz, Q2));   // (-tn, tf)
     miss = shift_in_sign(miss, h2_lane_sum(m));                  // sign(tf - tn)
   }
-  return expand_hit_bits(~miss & 0xffu, im, n1.z, n1.w);
+  return ~miss & 0xffu;
+}
+AOB_D uint32_t intersect_node8_h2(const U4* nodes, uint32_t idx, const RayState& r, uint32_t* child_base, uint32_t* prim_base,
+                                  uint32_t* imask) {
+  uint32_t mlo, mhi;
+  const uint32_t hb = intersect_node8_h2_raw(nodes, idx, r, child_base, prim_base, imask, &mlo, &mhi);
+  return expand_hit_bits(hb, *imask, mlo, mhi);
+}
+// The leaf slots `lh` (bits 0..7) of node `idx`: primitive base and the 24-bit primitive mask relative to it.  The fused
+// kernel keeps (node, hit leaf slots) while a lane is paused and expands them here, inside the batched block, instead of
+// after every node test (the expansion loop runs for two lanes at a time there).
+AOB_D uint32_t leaf_slots_to_prims(const U4* nodes, uint32_t idx, uint32_t lh, uint32_t* prim_base) {
+  const U4 n1 = ld_u4(nodes + 5ull * idx + 1);
+  *prim_base = n1.y;
+  uint32_t mask = 0;
+  while (lh) {
+    const int s = ffs32(lh) - 1;
+    lh &= lh - 1u;
+    const uint32_t m = (((s & 4) ? n1.w : n1.z) >> (8 * (s & 3))) & 0xffu;
+    mask |= (m >> 5) << (m & 31u);
+  }
+  return mask;
 }
 
 struct TraceCounters {

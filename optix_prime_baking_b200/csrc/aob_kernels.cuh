@@ -577,7 +577,7 @@ AOB_D void defer_ray(const DeferredRays& D, uint32_t rel, uint32_t pass) {
 }
 
 template <bool STATS, bool TWO_LEVEL, bool CLAMP_TMAX, bool H2>
-__global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleView S, uint64_t begin, uint32_t n, int q, float offset,
+__global__ void __launch_bounds__(kAoBlock, 7) k_ao_persistent(BvhView bvh, SampleView S, uint64_t begin, uint32_t n, int q, float offset,
                                                              float maxdist, uint32_t n_chunks, uint32_t refill_below, uint32_t tri_batch,
                                                              uint32_t part, uint32_t num_parts, uint32_t sb_blocks, uint32_t n_local_blocks,
                                                              uint32_t* __restrict__ hits, unsigned long long* __restrict__ counter,
@@ -744,13 +744,14 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
           const uint32_t slot = (uint32_t)bit - 24u;
           const uint32_t node = G.x + (uint32_t)__popc(G.y & 0xffu & ((1u << slot) - 1u));
           if (G.y & 0xff000000u) push(sp, G);
-          uint32_t cb, pb, im;
-          const uint32_t hm = H2 ? intersect_node8_h2(bvh.nodes, node, r, &cb, &pb, &im) : intersect_node8<CLAMP_TMAX>(bvh.nodes, node, r, nc, &cb, &pb, &im);
+          uint32_t cb, pb, im, mlo, mhi;
+          const uint32_t hb = H2 ? intersect_node8_h2_raw(bvh.nodes, node, r, &cb, &pb, &im, &mlo, &mhi)
+                                 : intersect_node8_raw<CLAMP_TMAX>(bvh.nodes, node, r, nc, &cb, &pb, &im, &mlo, &mhi);
           if (STATS) c_nodes++;
-          G.x = cb; G.y = (hm & 0xff000000u) | im;
-          T.x = pb; T.y = hm & 0x00ffffffu;
+          G.x = cb; G.y = ((hb & im) << 24) | im;
+          T.x = node; T.y = hb & ~im;   // (node, hit leaf slots): expanded to primitives when the block runs
         } else if (TWO_LEVEL) {
-          T = G;  // a postponed TLAS primitive group
+          T = G;  // a postponed TLAS primitive group (node, leaf slots left)
           G.x = 0; G.y = 0;
         }
         // leaf hits (triangles inside a BLAS / a flattened scene, instances in a TLAS) are not processed at once: the
@@ -767,16 +768,21 @@ __global__ void __launch_bounds__(kAoBlock) k_ao_persistent(BvhView bvh, SampleV
           if (paused) {
             paused = false;
             if (in_blas) {
-              uint32_t tested = 0;
-              hit = test_tri_group(bvh.tris, T.x, T.y, r.org, r.dir, 0.0f, maxdist, &tested);
+              uint32_t tested = 0, pbase;
+              const uint32_t pmask = leaf_slots_to_prims(bvh.nodes, T.x, T.y, &pbase);
+              hit = test_tri_group(bvh.tris, pbase, pmask, r.org, r.dir, 0.0f, maxdist, &tested);
               if (STATS) c_tris += tested;
             } else if (TWO_LEVEL) {
-              // instances of the group: skip those whose bounding sphere the world ray cannot touch,
-              // enter the first one it can — save the TLAS continuation, switch to object space
+              // instances of the group (one per TLAS leaf slot): skip those whose bounding sphere the world ray
+              // cannot touch, enter the first one it can — save the TLAS continuation, switch to object space
+              // (the node's primitive base and meta bytes are re-read per slot, L1 hits, rather than held in registers:
+              //  this kernel has none to spare)
+              const uint32_t* tn1 = reinterpret_cast<const uint32_t*>(bvh.nodes + 5ull * T.x + 1);
               while (T.y) {
-                const int b = __ffs((int)T.y) - 1;
+                const int sl = __ffs((int)T.y) - 1;
                 T.y &= T.y - 1u;
-                const F4* rec = bvh.insts + (uint64_t)kInstF4 * ((uint64_t)T.x + (uint32_t)b);
+                const uint32_t b = (__ldg(tn1 + 2 + (sl >> 2)) >> (8 * (sl & 3))) & 31u;   // offset of the slot's instance
+                const F4* rec = bvh.insts + (uint64_t)kInstF4 * ((uint64_t)__ldg(tn1 + 1) + b);
                 if (!sphere_may_hit(org, wdir, ld_f4(rec + 4))) continue;
                 if (T.y) push(sp, T);
                 if (G.y & 0xff000000u) push(sp, G);
