@@ -38,7 +38,7 @@ def func_ranges(path, names):
 
 
 csrc = ROOT + "/optix_prime_baking_b200/csrc/"
-bvh = func_ranges(csrc + "aob_bvh.cuh", {"node": r"uint32_t intersect_node8_h2\(", "node32": r"uint32_t intersect_node8\(const U4",
+bvh = func_ranges(csrc + "aob_bvh.cuh", {"node": r"uint32_t intersect_node8_h2(_raw)?\(", "node32": r"uint32_t intersect_node8(_raw)?\(const U4", "leafslots": r"uint32_t leaf_slots_to_prims\(",
                                          "expand": r"uint32_t expand_hit_bits\(", "tri_k": r"bool test_tri_group_k\(", "tri_sel": r"bool test_tri_group_sel\(",
                                          "tri": r"bool test_tri_group\(const F4", "sphere": r"bool sphere_may_hit\(", "rcp": r"float safe_rcp\("})
 mth = func_ranges(csrc + "aob_math.cuh", {"tea": r"uint32_t tea\(", "lcg": r"uint32_t lcg\(", "rnd": r"float rnd\(", "sincos": r"void sincos2pi\(",
@@ -65,8 +65,9 @@ def classify(f, ln):
         for k in ("node", "node32"):
             if k in bvh and bvh[k][0] <= ln <= bvh[k][1]:
                 return "node test"
-        if "expand" in bvh and bvh["expand"][0] <= ln <= bvh["expand"][1]:
-            return "leaf-mask expansion"
+        for k in ("expand", "leafslots"):
+            if k in bvh and bvh[k][0] <= ln <= bvh[k][1]:
+                return "leaf-mask expansion"
         for k in ("tri_k", "tri_sel", "tri"):
             if k in bvh and bvh[k][0] <= ln <= bvh[k][1]:
                 return "triangle block"
