@@ -552,6 +552,10 @@ __global__ void __launch_bounds__(256) k_ao_simple(BvhView bvh, SampleView S, ui
 //     ([depth][thread] columns, AOB_SM_STACK entries) is available but measured slower;
 //   * the Woop shear constants are computed lazily, only by lanes that reach a triangle.
 constexpr int kAoBlock = 128;
+#ifndef AOB_LOOKAHEAD
+#define AOB_LOOKAHEAD 1
+#endif
+constexpr int kLookahead = AOB_LOOKAHEAD;   // rays a lane keeps queued (generated converged at a refill)
 // Entries of the traversal stack kept in shared memory ([depth][thread] columns); the rest lives in
 // local memory.  Measured on B200 (profiles/r1/sweep_stack_placement.log): 0 — the whole stack in
 // L1-resident local memory — is fastest (config 2: 12.87 vs 12.24 Grays/s with 6, config 3: 7.13 vs
@@ -612,8 +616,8 @@ __global__ void __launch_bounds__(kAoBlock, 7) k_ao_persistent(BvhView bvh, Samp
 
   const NodeConsts nc = make_node_consts();
   // per-lane item state
-  __shared__ float s_la[6][kAoBlock];  // queued (lookahead) ray per thread: direction + slab reciprocals
-  bool la_valid = false;
+  __shared__ float s_la[kLookahead][6][kAoBlock];  // queued (lookahead) rays per thread: direction + slab reciprocals
+  uint32_t la_count = 0, la_head = 0;              // rays queued; slot of the oldest
   bool have_item = false, ray_active = false, exhausted = false;
   uint32_t rel = 0, pass = 0, pass_end = 0, nh = 0;
   uint32_t supply_next = 0, supply_left = 0, supply_chunk = 0;  // warp-uniform
@@ -642,10 +646,12 @@ __global__ void __launch_bounds__(kAoBlock, 7) k_ao_persistent(BvhView bvh, Samp
   const unsigned long long n_global_blocks = ((unsigned long long)n + 31ull) / 32ull;
   const unsigned long long total_items = n_blocks * n_chunks;  // item = (block of 32 samples, strata chunk)
   auto start_queued = [&]() {
-    wdir = v3(s_la[0][threadIdx.x], s_la[1][threadIdx.x], s_la[2][threadIdx.x]);
-    la_valid = false;
+    const float(*la)[kAoBlock] = s_la[la_head];
+    wdir = v3(la[0][threadIdx.x], la[1][threadIdx.x], la[2][threadIdx.x]);
+    la_head = la_head + 1 == kLookahead ? 0u : la_head + 1;
+    la_count--;
     r.org = org; r.dir = wdir;
-    r.idir = v3(s_la[3][threadIdx.x], s_la[4][threadIdx.x], s_la[5][threadIdx.x]);
+    r.idir = v3(la[3][threadIdx.x], la[4][threadIdx.x], la[5][threadIdx.x]);
     in_blas = !TWO_LEVEL;
     G.x = bvh.root;
     G.y = (1u << 24) | 1u;
@@ -655,7 +661,7 @@ __global__ void __launch_bounds__(kAoBlock, 7) k_ao_persistent(BvhView bvh, Samp
 
   while (true) {
     // ------------------------------ refill ------------------------------
-    if (!ray_active && !la_valid && have_item && pass == pass_end) {
+    if (!ray_active && la_count == 0u && have_item && pass == pass_end) {
       if (n_chunks > 1) atomicAdd(&hits[rel], nh);
       else hits[rel] = nh;
       have_item = false;
@@ -699,26 +705,34 @@ __global__ void __launch_bounds__(kAoBlock, 7) k_ao_persistent(BvhView bvh, Samp
       supply_next += take;
       supply_left -= take;
     }
-    // One-deep lookahead: at a refill *every* lane without a queued ray generates its next one
-    // (idle lanes and lanes still traversing alike), so ray generation runs with most of the
-    // warp converged instead of only the few idle lanes; a lane whose ray ends inside the
-    // traversal loop starts its queued ray at once, without a refill.
-    if (have_item && !la_valid && pass < pass_end) {
-      const uint64_t gf = 3ull * (begin + rel);
-      const V3 fnrm = v3(__ldg(S.fnrm + gf), __ldg(S.fnrm + gf + 1), __ldg(S.fnrm + gf + 2));
-      const V3 nrm = v3(__ldg(S.nrm + gf), __ldg(S.nrm + gf + 1), __ldg(S.nrm + gf + 2));
-      const V3 d = ao_ray_dir((uint32_t)(begin + rel), pass, q, nrm, fnrm, onb);
-      const V3 id = v3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
-      if (H2 && !(fmaxf(fmaxf(fabsf(id.x), fabsf(id.y)), fabsf(id.z)) <= kH2MaxIdir)) {
-        defer_ray(deferred, rel, pass);   // world rays are unit length: only the reciprocal can disqualify them
-      } else {
-        s_la[0][threadIdx.x] = d.x; s_la[1][threadIdx.x] = d.y; s_la[2][threadIdx.x] = d.z;
-        s_la[3][threadIdx.x] = id.x; s_la[4][threadIdx.x] = id.y; s_la[5][threadIdx.x] = id.z;
-        la_valid = true;
+    // Lookahead: at a refill *every* lane whose queue has room generates rays for it (idle lanes and lanes still
+    // traversing alike), so ray generation runs with most of the warp converged instead of only the few idle lanes; a
+    // lane whose ray ends inside the traversal loop starts its oldest queued ray at once, without a refill.  A queue of
+    // kLookahead = 2 halves the number of refills: a lane goes idle only after using up both, by which time most of
+    // the warp has room for at least one.
+    for (int rep = 0; rep < kLookahead; rep++) {
+      const bool gen = have_item && la_count < (uint32_t)kLookahead && pass < pass_end;
+      if (kLookahead > 1 && !__any_sync(0xffffffffu, gen)) break;
+      if (gen) {
+        const uint64_t gf = 3ull * (begin + rel);
+        const V3 fnrm = v3(__ldg(S.fnrm + gf), __ldg(S.fnrm + gf + 1), __ldg(S.fnrm + gf + 2));
+        const V3 nrm = v3(__ldg(S.nrm + gf), __ldg(S.nrm + gf + 1), __ldg(S.nrm + gf + 2));
+        const V3 d = ao_ray_dir((uint32_t)(begin + rel), pass, q, nrm, fnrm, onb);
+        const V3 id = v3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
+        if (H2 && !(fmaxf(fmaxf(fabsf(id.x), fabsf(id.y)), fabsf(id.z)) <= kH2MaxIdir)) {
+          defer_ray(deferred, rel, pass);   // world rays are unit length (the host checks the normals): only the reciprocal can disqualify them
+        } else {
+          uint32_t slot = la_head + la_count;
+          if (slot >= (uint32_t)kLookahead) slot -= (uint32_t)kLookahead;
+          float(*la)[kAoBlock] = s_la[slot];
+          la[0][threadIdx.x] = d.x; la[1][threadIdx.x] = d.y; la[2][threadIdx.x] = d.z;
+          la[3][threadIdx.x] = id.x; la[4][threadIdx.x] = id.y; la[5][threadIdx.x] = id.z;
+          la_count++;
+        }
+        pass++;
       }
-      pass++;
     }
-    if (!ray_active && la_valid) start_queued();
+    if (!ray_active && la_count != 0u) start_queued();
     if (!__any_sync(0xffffffffu, ray_active)) {
       if (exhausted && !__any_sync(0xffffffffu, have_item)) break;  // nothing in flight and nothing left
       continue;
@@ -825,7 +839,7 @@ __global__ void __launch_bounds__(kAoBlock, 7) k_ao_persistent(BvhView bvh, Samp
         nh += hit ? 1u : 0u;
         if (done) {
           ray_active = false;
-          if (la_valid) start_queued();
+          if (la_count != 0u) start_queued();
         }
       }
       act = __ballot_sync(0xffffffffu, ray_active);   // (unchanged until the end of the next iteration: reused by the pause test)
