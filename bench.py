@@ -100,6 +100,9 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t0 = time.perf_counter()
+        while len(self.lines) < 3 and time.perf_counter() - t0 < 1.5:   # a timed region shorter than the sampling period
+            time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
