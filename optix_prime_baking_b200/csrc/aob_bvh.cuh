@@ -413,6 +413,61 @@ AOB_HD void collapse_body(uint32_t w, const CollapseArgs& A) {
   A.nodes[A.node_offset + w] = nd;
 }
 
+// ---- oversized primitives (see k_flag_big in aob_kernels.cuh) ---------------------------
+// A primitive is oversized when its box is longer than a quarter of the scene's largest extent.
+AOB_HD bool box_is_oversized(F4 lo, F4 hi, float scene_extent) {
+  const float pe = fmaxf(hi.x - lo.x, fmaxf(hi.y - lo.y, hi.z - lo.z));
+  return pe > 0.25f * scene_extent;
+}
+// The extra root: slot 0 = the tree over the ordinary primitives (node `main_root`, box [small_lo, small_hi]), the
+// following slots = the oversized primitives (sorted positions [n_small, n_small + n_big), `per_slot` per slot), which
+// also complete the leaf order.  Shared by k_super_root and the CPU emulation.
+AOB_HD void super_root_body(Node8* out, uint32_t main_root, F4 nlo, F4 nhi, F4 small_lo, F4 small_hi, const F4* plo, const F4* phi,
+                            const uint32_t* sorted_prims, uint32_t n_small, uint32_t n_big, uint32_t per_slot, uint32_t prim_offset,
+                            uint32_t* leaf_prims) {
+  Node8 nd;
+  nd.px = nlo.x; nd.py = nlo.y; nd.pz = nlo.z;
+  uint32_t ex = quant_exponent(nhi.x - nlo.x), ey = quant_exponent(nhi.y - nlo.y), ez = quant_exponent(nhi.z - nlo.z);
+  {
+    uint32_t em = ex > ey ? ex : ey;   // same rule as collapse_body: steps within 2^kExpSpread of the widest
+    em = em > ez ? em : ez;
+    if (em < 24u) em = 24u;
+    const uint32_t fl = em - (uint32_t)kExpSpread;
+    ex = ex > fl ? ex : fl; ey = ey > fl ? ey : fl; ez = ez > fl ? ez : fl;
+  }
+  nd.ex = (uint8_t)ex; nd.ey = (uint8_t)ey; nd.ez = (uint8_t)ez;
+  nd.child_base = main_root;
+  nd.prim_base = prim_offset + n_small;
+  nd.imask = 1u;
+  for (int k = 0; k < 8; k++) {
+    nd.meta[k] = 0;
+    for (int a = 0; a < 3; a++) { nd.q[a][k][0] = 255; nd.q[a][k][1] = 0; }
+  }
+  nd.meta[0] = (uint8_t)(0x20u | 24u);
+  quantize_axis(nlo.x, ex, small_lo.x, small_hi.x, &nd.q[0][0][0], &nd.q[0][0][1]);
+  quantize_axis(nlo.y, ey, small_lo.y, small_hi.y, &nd.q[1][0][0], &nd.q[1][0][1]);
+  quantize_axis(nlo.z, ez, small_lo.z, small_hi.z, &nd.q[2][0][0], &nd.q[2][0][1]);
+  uint32_t po = 0;
+  for (uint32_t k = 1; k < 8 && po < n_big; k++) {
+    const uint32_t cnt = per_slot < n_big - po ? per_slot : n_big - po;
+    F4 lo, hi;
+    lo.x = lo.y = lo.z = 3.0e38f; hi.x = hi.y = hi.z = -3.0e38f;
+    lo.w = hi.w = 0.f;
+    for (uint32_t j = 0; j < cnt; j++) {
+      const uint32_t p = sorted_prims[n_small + po + j];
+      leaf_prims[n_small + po + j] = p;
+      lo.x = fminf(lo.x, plo[p].x); lo.y = fminf(lo.y, plo[p].y); lo.z = fminf(lo.z, plo[p].z);
+      hi.x = fmaxf(hi.x, phi[p].x); hi.y = fmaxf(hi.y, phi[p].y); hi.z = fmaxf(hi.z, phi[p].z);
+    }
+    quantize_axis(nlo.x, ex, lo.x, hi.x, &nd.q[0][k][0], &nd.q[0][k][1]);
+    quantize_axis(nlo.y, ey, lo.y, hi.y, &nd.q[1][k][0], &nd.q[1][k][1]);
+    quantize_axis(nlo.z, ez, lo.z, hi.z, &nd.q[2][k][0], &nd.q[2][k][1]);
+    nd.meta[k] = (uint8_t)((((1u << cnt) - 1u) << 5) | po);
+    po += cnt;
+  }
+  *out = nd;
+}
+
 // =======================================================================================
 // Traversal
 // =======================================================================================

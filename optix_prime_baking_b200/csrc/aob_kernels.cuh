@@ -178,9 +178,7 @@ __global__ void k_flag_big(const F4* __restrict__ plo, const F4* __restrict__ ph
   const float sx = ordered_to_float(f6[3]) - ordered_to_float(f6[0]), sy = ordered_to_float(f6[4]) - ordered_to_float(f6[1]),
               sz = ordered_to_float(f6[5]) - ordered_to_float(f6[2]);
   const float ext = fmaxf(sx, fmaxf(sy, sz));
-  const F4 lo = plo[i], hi = phi[i];
-  const float pe = fmaxf(hi.x - lo.x, fmaxf(hi.y - lo.y, hi.z - lo.z));
-  const bool b = pe > 0.25f * ext;
+  const bool b = box_is_oversized(plo[i], phi[i], ext);
   big[i] = b ? 1 : 0;
   if (b) atomicAdd(count, 1u);
 }
@@ -226,49 +224,12 @@ __global__ void k_super_root(Node8* __restrict__ nodes, uint32_t node_index, uin
                              const uint32_t* __restrict__ sorted_prims, uint32_t n_small, uint32_t n_big, uint32_t per_slot,
                              uint32_t prim_offset, uint32_t* __restrict__ leaf_prims) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  F4 nlo, nhi;
+  F4 nlo, nhi, slo, shi;
   nlo.x = ordered_to_float(f6_all[0]); nlo.y = ordered_to_float(f6_all[1]); nlo.z = ordered_to_float(f6_all[2]); nlo.w = 0.f;
   nhi.x = ordered_to_float(f6_all[3]); nhi.y = ordered_to_float(f6_all[4]); nhi.z = ordered_to_float(f6_all[5]); nhi.w = 0.f;
-  Node8 nd;
-  nd.px = nlo.x; nd.py = nlo.y; nd.pz = nlo.z;
-  uint32_t ex = quant_exponent(nhi.x - nlo.x), ey = quant_exponent(nhi.y - nlo.y), ez = quant_exponent(nhi.z - nlo.z);
-  {
-    uint32_t em = ex > ey ? ex : ey;   // same rule as collapse_body: steps within 2^kExpSpread of the widest
-    em = em > ez ? em : ez;
-    if (em < 24u) em = 24u;
-    const uint32_t fl = em - (uint32_t)kExpSpread;
-    ex = ex > fl ? ex : fl; ey = ey > fl ? ey : fl; ez = ez > fl ? ez : fl;
-  }
-  nd.ex = (uint8_t)ex; nd.ey = (uint8_t)ey; nd.ez = (uint8_t)ez;
-  nd.child_base = main_root;
-  nd.prim_base = prim_offset + n_small;
-  nd.imask = 1u;
-  for (int k = 0; k < 8; k++) {
-    nd.meta[k] = 0;
-    for (int a = 0; a < 3; a++) { nd.q[a][k][0] = 255; nd.q[a][k][1] = 0; }
-  }
-  nd.meta[0] = (uint8_t)(0x20u | 24u);
-  quantize_axis(nlo.x, ex, ordered_to_float(f6_small[0]), ordered_to_float(f6_small[3]), &nd.q[0][0][0], &nd.q[0][0][1]);
-  quantize_axis(nlo.y, ey, ordered_to_float(f6_small[1]), ordered_to_float(f6_small[4]), &nd.q[1][0][0], &nd.q[1][0][1]);
-  quantize_axis(nlo.z, ez, ordered_to_float(f6_small[2]), ordered_to_float(f6_small[5]), &nd.q[2][0][0], &nd.q[2][0][1]);
-  uint32_t po = 0;
-  for (uint32_t k = 1; k < 8 && po < n_big; k++) {
-    const uint32_t cnt = min(per_slot, n_big - po);
-    F4 lo, hi;
-    lo.x = lo.y = lo.z = 3.0e38f; hi.x = hi.y = hi.z = -3.0e38f;
-    for (uint32_t j = 0; j < cnt; j++) {
-      const uint32_t p = sorted_prims[n_small + po + j];
-      leaf_prims[n_small + po + j] = p;
-      lo.x = fminf(lo.x, plo[p].x); lo.y = fminf(lo.y, plo[p].y); lo.z = fminf(lo.z, plo[p].z);
-      hi.x = fmaxf(hi.x, phi[p].x); hi.y = fmaxf(hi.y, phi[p].y); hi.z = fmaxf(hi.z, phi[p].z);
-    }
-    quantize_axis(nlo.x, ex, lo.x, hi.x, &nd.q[0][k][0], &nd.q[0][k][1]);
-    quantize_axis(nlo.y, ey, lo.y, hi.y, &nd.q[1][k][0], &nd.q[1][k][1]);
-    quantize_axis(nlo.z, ez, lo.z, hi.z, &nd.q[2][k][0], &nd.q[2][k][1]);
-    nd.meta[k] = (uint8_t)((((1u << cnt) - 1u) << 5) | po);
-    po += cnt;
-  }
-  nodes[node_index] = nd;
+  slo.x = ordered_to_float(f6_small[0]); slo.y = ordered_to_float(f6_small[1]); slo.z = ordered_to_float(f6_small[2]); slo.w = 0.f;
+  shi.x = ordered_to_float(f6_small[3]); shi.y = ordered_to_float(f6_small[4]); shi.z = ordered_to_float(f6_small[5]); shi.w = 0.f;
+  super_root_body(nodes + node_index, main_root, nlo, nhi, slo, shi, plo, phi, sorted_prims, n_small, n_big, per_slot, prim_offset, leaf_prims);
 }
 __global__ void k_hierarchy(Lbvh L) { lbvh_hierarchy_body(blockIdx.x * blockDim.x + threadIdx.x, L); }
 __global__ void k_refit(Lbvh L) { lbvh_refit_body(blockIdx.x * blockDim.x + threadIdx.x, L); }

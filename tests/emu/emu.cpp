@@ -15,6 +15,7 @@ using namespace aob;
 
 static int g_node_test_fp32 = 0;              // 1: fp32 node test for every ray (cross-check of the fp16 test)
 static uint32_t g_max_leaf_override = 0;   // experiments: leaf slot capacity (0 = builder default)
+static int g_no_oversized_split = 0;       // 1: keep oversized primitives in the tree (AoBakeParams::no_oversized_split)
 
 struct EmuBvh {
   std::vector<Node8> nodes;
@@ -26,9 +27,50 @@ struct EmuBvh {
 
 // Builds one BVH segment over `n` boxes appended at nodes.size(); returns root index and
 // fills leaf_prims (leaf order -> primitive id).
+static uint32_t build_tree(const std::vector<F4>& plo, const std::vector<F4>& phi, const std::vector<uint32_t>& subset, uint32_t max_leaf,
+                           uint32_t prim_offset, std::vector<Node8>& nodes, std::vector<uint32_t>& leaf_prims);
+
+// Builds one BVH segment over `n` boxes appended at nodes.size(); returns root index and fills leaf_prims (leaf order ->
+// primitive id).  Mirrors build_segment of aobake.cu, including the split of oversized primitives onto an extra root.
 static uint32_t build_segment(const std::vector<F4>& plo, const std::vector<F4>& phi, uint32_t max_leaf,
                               uint32_t prim_offset, std::vector<Node8>& nodes, std::vector<uint32_t>& leaf_prims) {
   const uint32_t n = (uint32_t)plo.size();
+  std::vector<uint32_t> small, big;
+  F4 alo, ahi, slo, shi;
+  alo.x = alo.y = alo.z = slo.x = slo.y = slo.z = 3.0e38f; ahi.x = ahi.y = ahi.z = shi.x = shi.y = shi.z = -3.0e38f;
+  alo.w = ahi.w = slo.w = shi.w = 0.f;
+  for (uint32_t i = 0; i < n; i++) {
+    alo.x = fminf(alo.x, plo[i].x); alo.y = fminf(alo.y, plo[i].y); alo.z = fminf(alo.z, plo[i].z);
+    ahi.x = fmaxf(ahi.x, phi[i].x); ahi.y = fmaxf(ahi.y, phi[i].y); ahi.z = fmaxf(ahi.z, phi[i].z);
+  }
+  const float ext = n ? fmaxf(ahi.x - alo.x, fmaxf(ahi.y - alo.y, ahi.z - alo.z)) : 0.f;
+  for (uint32_t i = 0; i < n; i++) (box_is_oversized(plo[i], phi[i], ext) ? big : small).push_back(i);
+  const uint32_t per_slot = std::max(1u, std::min(max_leaf, 3u));
+  const bool split = !g_no_oversized_split && !big.empty() && big.size() < n && big.size() <= 7u * per_slot;
+  if (!split) {
+    std::vector<uint32_t> all(n);
+    std::iota(all.begin(), all.end(), 0u);
+    return build_tree(plo, phi, all, max_leaf, prim_offset, nodes, leaf_prims);
+  }
+  for (uint32_t i : small) {
+    slo.x = fminf(slo.x, plo[i].x); slo.y = fminf(slo.y, plo[i].y); slo.z = fminf(slo.z, plo[i].z);
+    shi.x = fmaxf(shi.x, phi[i].x); shi.y = fmaxf(shi.y, phi[i].y); shi.z = fmaxf(shi.z, phi[i].z);
+  }
+  const uint32_t main_root = build_tree(plo, phi, small, max_leaf, prim_offset, nodes, leaf_prims);
+  std::vector<uint32_t> sorted(small);          // positions [n_small, n) = the oversized primitives, in index order (stable sort of key ~0)
+  sorted.insert(sorted.end(), big.begin(), big.end());
+  leaf_prims.resize(n);
+  Node8 nd;
+  super_root_body(&nd, main_root, alo, ahi, slo, shi, plo.data(), phi.data(), sorted.data(), (uint32_t)small.size(), (uint32_t)big.size(), per_slot,
+                  prim_offset, leaf_prims.data());
+  nodes.push_back(nd);
+  return (uint32_t)nodes.size() - 1;
+}
+
+// One LBVH -> 8-wide tree over the primitives listed in `subset`; leaf_prims gets subset.size() entries.
+static uint32_t build_tree(const std::vector<F4>& plo, const std::vector<F4>& phi, const std::vector<uint32_t>& subset, uint32_t max_leaf,
+                           uint32_t prim_offset, std::vector<Node8>& nodes, std::vector<uint32_t>& leaf_prims) {
+  const uint32_t n = (uint32_t)subset.size();
   const uint32_t node_offset = (uint32_t)nodes.size();
   leaf_prims.assign(n, 0);
   if (n == 0) {
@@ -39,7 +81,7 @@ static uint32_t build_segment(const std::vector<F4>& plo, const std::vector<F4>&
     return node_offset;
   }
   V3 cmin = v3(1e30f, 1e30f, 1e30f), cmax = v3(-1e30f, -1e30f, -1e30f);
-  for (uint32_t i = 0; i < n; i++) {
+  for (uint32_t i : subset) {
     float cx = 0.5f * (plo[i].x + phi[i].x), cy = 0.5f * (plo[i].y + phi[i].y), cz = 0.5f * (plo[i].z + phi[i].z);
     cmin = v3(fminf(cmin.x, cx), fminf(cmin.y, cy), fminf(cmin.z, cz));
     cmax = v3(fmaxf(cmax.x, cx), fmaxf(cmax.y, cy), fmaxf(cmax.z, cz));
@@ -48,12 +90,12 @@ static uint32_t build_segment(const std::vector<F4>& plo, const std::vector<F4>&
   const float inv = ext > 0.0f ? 1.0f / ext : 0.0f;
   V3 cinv = v3(inv, inv, inv);
   std::vector<uint64_t> keys(n);
-  std::vector<uint32_t> order(n);
-  for (uint32_t i = 0; i < n; i++) keys[i] = morton63(plo[i], phi[i], cmin, cinv);
-  std::iota(order.begin(), order.end(), 0u);
-  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+  std::vector<uint32_t> pos(n), order(n);
+  for (uint32_t k = 0; k < n; k++) keys[k] = morton63(plo[subset[k]], phi[subset[k]], cmin, cinv);
+  std::iota(pos.begin(), pos.end(), 0u);
+  std::stable_sort(pos.begin(), pos.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
   std::vector<uint64_t> skeys(n);
-  for (uint32_t i = 0; i < n; i++) skeys[i] = keys[order[i]];
+  for (uint32_t k = 0; k < n; k++) { skeys[k] = keys[pos[k]]; order[k] = subset[pos[k]]; }
   const uint32_t ni = n > 1 ? n - 1 : 1;
   std::vector<uint32_t> left(ni), right(ni), first(ni), last(ni), pint(ni), pleaf(n), flags(ni, 0), wide2bin(n), count(ni, 0);
   std::vector<F4> ilo(ni), ihi(ni);
@@ -180,6 +222,7 @@ void* emu_bvh_create_two_level(uint32_t num_meshes, const float* const* mesh_tri
 
 void emu_set_max_leaf(uint32_t m) { g_max_leaf_override = m; }
 void emu_set_node_test_fp32(int on) { g_node_test_fp32 = on; }
+void emu_set_no_oversized_split(int on) { g_no_oversized_split = on; }
 void emu_bvh_destroy(void* h) { delete static_cast<EmuBvh*>(h); }
 uint64_t emu_bvh_num_nodes(void* h) { return static_cast<EmuBvh*>(h)->nodes.size(); }
 

@@ -231,3 +231,24 @@ def test_single_rank_communicator_and_distributed_entry_points(api):
         b.comm_destroy()
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
     assert np.abs(got_v[0] - want_v[0]).max() < 1e-6
+
+
+@pytest.mark.parametrize("energy", [0, 1])
+def test_least_squares_mid_size_solution_against_the_oracle(api, energy):
+    """The solutions themselves (not residuals) at a size the oracle still solves in seconds: a 320 k-triangle warped
+    heightfield with a ground plane, half of it unsampled, both regulariser forms, assembled-matrix product."""
+    scene, _ = scenes.config3_bigmesh(400, seed=3)
+    blockers = scenes.ground_blockers(scene)
+    off, maxd = scenes.default_distances(scene)
+    with api.Baker(ls_energy=energy, cg_tolerance=1e-8) as bk:
+        bk.set_scene(scene, blockers)
+        total, per = bk.distribute_samples(0, scene.num_triangles // 2)
+        sb = bk.sample_instances(per, 0)
+        ao = bk.compute_ao(64, off, maxd)
+        v = bk.map_ao_to_vertices(api.FILTER_LEAST_SQUARES, 0.1)[0]
+        iters = bk.timings().cg_iterations
+        assert bk.stats().reserved[3] == 1
+    orc = Oracle(scene, blockers)
+    ov = orc.filter_least_squares(sb, ao, 0.1, tol=1e-8, per_instance=per, energy=energy)[0]
+    assert np.abs(v - ov).max() <= VERTEX_AO_TOL
+    assert abs(iters - orc.ls_iterations) <= 8 + 0.02 * orc.ls_iterations      # same method, same system: same count (the GPU checks every 8)

@@ -198,6 +198,33 @@ def test_emulated_kernels_match_oracle(emu):
         assert np.array_equal(hit, orc.trace_rays(rays)), name
 
 
+def test_emulated_oversized_primitives_on_an_extra_root(emu):
+    """The builder's split of oversized primitives (the ground-plane quad under a fine mesh: aob_kernels.cuh
+    k_flag_big / k_super_root, emulated through the shared bodies): identical hit/miss decisions with and without
+    the split, both equal to the oracle, and fewer node visits with it."""
+    sc, _ = scenes.config3_bigmesh(60, seed=3)
+    blk = scenes.ground_blockers(sc)
+    orc = Oracle(sc, blk)
+    _, per = orc.distribute_samples(1, 0)
+    sb = orc.sample_instances(per, 1)
+    off, md = scenes.default_distances(sc)
+    rays = np.ascontiguousarray(np.concatenate([orc.generate_rays(sb, 0, min(sb.n, 2000), 16, off, md).reshape(-1, 8), _random_rays(sc, 4000, 3)]),
+                                dtype=np.float32)
+    wt = _world_tris([sc, blk])
+    want = orc.trace_rays(rays)
+    visits = {}
+    for off_switch in (0, 1):
+        emu.emu_set_no_oversized_split(off_switch)
+        B = emu.emu_bvh_create_flat(wt.ctypes.data, len(wt))
+        hit = np.zeros(len(rays), dtype=np.uint8)
+        emu.emu_trace.restype = C.c_uint64
+        visits[off_switch] = emu.emu_trace(B, rays.ctypes.data, len(rays), hit.ctypes.data, None)
+        emu.emu_bvh_destroy(B)
+        assert np.array_equal(hit, want), off_switch
+    emu.emu_set_no_oversized_split(0)
+    assert visits[0] < 0.8 * visits[1]      # the extra root keeps the coarse grid out of the tree
+
+
 def test_emulated_two_level_matches_oracle(emu):
     scene, blk = scenes.config4_instanced(grid=2, stacks=10, slices=10, with_ground=True)
     orc = Oracle(scene, blk, 2)
