@@ -643,6 +643,9 @@ AOB_D uint32_t intersect_node8(const U4* nodes, uint32_t idx, const RayState& r,
 #ifndef AOB_H2_CORNER_FRAME
 #define AOB_H2_CORNER_FRAME 0
 #endif
+// CLAMP_TMAX = false drops the far clamp of the ray interval (legal whenever tmax exceeds the diagonal of the tree being
+// walked — the AO default: boxes beyond tmax cannot exist inside it, and the triangle test enforces t < tmax exactly).
+template <bool CLAMP_TMAX = true>
 AOB_D uint32_t intersect_node8_h2_raw(const U4* nodes, uint32_t idx, const RayState& r, uint32_t* child_base, uint32_t* prim_base,
                                       uint32_t* imask, uint32_t* meta_lo, uint32_t* meta_hi) {
   const U4* p = nodes + 5ull * idx;
@@ -675,8 +678,14 @@ AOB_D uint32_t intersect_node8_h2_raw(const U4* nodes, uint32_t idx, const RaySt
   // lanes: low = -(near plane), high = far plane
   const uint32_t A2x = h2_pack_sat(ax, -ax), A2y = h2_pack_sat(ay, -ay), A2z = h2_pack_sat(az, -az);
   const uint32_t B2x = h2_pack_sat(bx + px, px - bx), B2y = h2_pack_sat(by + py, py - by), B2z = h2_pack_sat(bz + pz, pz - bz);
-  const float q0 = (r.tmin - tc) * inv, q1 = (r.tmax - tc) * inv;
-  const uint32_t Q2 = h2_pack_sat(fmaf(5.2e-4f, fabsf(q1), q1 + 6.5e-8f), fmaf(5.2e-4f, fabsf(q0), 6.5e-8f - q0));
+  const float q0 = (r.tmin - tc) * inv;
+  uint32_t Q2;
+  if (CLAMP_TMAX) {
+    const float q1 = (r.tmax - tc) * inv;
+    Q2 = h2_pack_sat(fmaf(5.2e-4f, fabsf(q1), q1 + 6.5e-8f), fmaf(5.2e-4f, fabsf(q0), 6.5e-8f - q0));
+  } else {
+    Q2 = h2_pack_sat(65504.0f, fmaf(5.2e-4f, fabsf(q0), 6.5e-8f - q0));   // far lane: the largest finite half
+  }
   // byte selectors: (near byte, 0, far byte, 0) with RZ as the second PRMT source; slot 2j + 1 is +0x0202
   const uint32_t s0x = r.dir.x < 0.0f ? 0x4041u : 0x4140u, s0y = r.dir.y < 0.0f ? 0x4041u : 0x4140u,
                  s0z = r.dir.z < 0.0f ? 0x4041u : 0x4140u;
@@ -696,7 +705,7 @@ AOB_D uint32_t intersect_node8_h2_raw(const U4* nodes, uint32_t idx, const RaySt
 AOB_D uint32_t intersect_node8_h2(const U4* nodes, uint32_t idx, const RayState& r, uint32_t* child_base, uint32_t* prim_base,
                                   uint32_t* imask) {
   uint32_t mlo, mhi;
-  const uint32_t hb = intersect_node8_h2_raw(nodes, idx, r, child_base, prim_base, imask, &mlo, &mhi);
+  const uint32_t hb = intersect_node8_h2_raw<true>(nodes, idx, r, child_base, prim_base, imask, &mlo, &mhi);
   return expand_hit_bits(hb, *imask, mlo, mhi);
 }
 // The leaf slots `lh` (bits 0..7) of node `idx`: primitive base and the 24-bit primitive mask relative to it.  The fused

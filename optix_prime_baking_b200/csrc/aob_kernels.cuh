@@ -720,7 +720,7 @@ __global__ void __launch_bounds__(kAoBlock, 7) k_ao_persistent(BvhView bvh, Samp
           const uint32_t node = G.x + (uint32_t)__popc(G.y & 0xffu & ((1u << slot) - 1u));
           if (G.y & 0xff000000u) push(sp, G);
           uint32_t cb, pb, im, mlo, mhi;
-          const uint32_t hb = H2 ? intersect_node8_h2_raw(bvh.nodes, node, r, &cb, &pb, &im, &mlo, &mhi)
+          const uint32_t hb = H2 ? intersect_node8_h2_raw<CLAMP_TMAX>(bvh.nodes, node, r, &cb, &pb, &im, &mlo, &mhi)
                                  : intersect_node8_raw<CLAMP_TMAX>(bvh.nodes, node, r, nc, &cb, &pb, &im, &mlo, &mhi);
           if (STATS) c_nodes++;
           G.x = cb; G.y = ((hb & im) << 24) | im;

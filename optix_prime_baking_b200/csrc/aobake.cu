@@ -176,6 +176,7 @@ struct AoBake {
   uint32_t root = 0;
   bool two_level = false;
   float scene_diag = 0.f;   // diagonal of the world box of everything in the BVH
+  float main_diag = 0.f;    // diagonal of the box of the top-level tree without its oversized primitives (== scene_diag if none)
   AoStats stats{};
 
   // samples + AO
@@ -274,6 +275,7 @@ struct Segment {
   uint32_t node_count = 0;
   int levels = 1;  // depth of the 8-wide tree (collapse rounds) — bounds the traversal stack
   float box[6] = {0, 0, 0, 0, 0, 0};
+  float main_box[6] = {0, 0, 0, 0, 0, 0};   // box of the ordinary primitives (== box when nothing was split off)
 };
 
 // Builds one 8-wide BVH over n primitive boxes into d_nodes[node_offset...]; d_leaf_prims[n]
@@ -378,7 +380,14 @@ int build_segment(AoBake* ctx, const F4* d_plo, const F4* d_phi, uint32_t n, uin
     out->levels = levels + 1;
   }
   CK(cudaMemcpyAsync(out->box, d_box.p, sizeof(out->box), cudaMemcpyDeviceToHost, st));
+  if (split) {
+    k_decode_bounds<<<1, 32, 0, st>>>(d_bs.p + 6, d_box.p);
+    CKL();
+    CK(cudaStreamSynchronize(st));   // out->box has arrived before d_box is reused
+    CK(cudaMemcpyAsync(out->main_box, d_box.p, sizeof(out->main_box), cudaMemcpyDeviceToHost, st));
+  }
   CK(cudaStreamSynchronize(st));
+  if (!split) memcpy(out->main_box, out->box, sizeof(out->box));
   return AOBAKE_OK;
 }
 
@@ -733,6 +742,8 @@ static int set_scene_impl(AoBake* ctx, const AoScene* scene, const AoScene* bloc
     ctx->root = seg.root;
     ctx->scene_diag = n ? sqrtf((seg.box[3] - seg.box[0]) * (seg.box[3] - seg.box[0]) + (seg.box[4] - seg.box[1]) * (seg.box[4] - seg.box[1]) +
                                 (seg.box[5] - seg.box[2]) * (seg.box[5] - seg.box[2])) : 0.f;
+    ctx->main_diag = n ? sqrtf((seg.main_box[3] - seg.main_box[0]) * (seg.main_box[3] - seg.main_box[0]) + (seg.main_box[4] - seg.main_box[1]) * (seg.main_box[4] - seg.main_box[1]) +
+                               (seg.main_box[5] - seg.main_box[2]) * (seg.main_box[5] - seg.main_box[2])) : 0.f;
     ctx->stats.num_bvh_nodes = seg.node_count;
     ctx->stats.num_bvh_triangles = n;
   } else {
@@ -872,6 +883,8 @@ static int set_scene_impl(AoBake* ctx, const AoScene* scene, const AoScene* bloc
     ctx->root = tl.root;
     ctx->scene_diag = nI ? sqrtf((tl.box[3] - tl.box[0]) * (tl.box[3] - tl.box[0]) + (tl.box[4] - tl.box[1]) * (tl.box[4] - tl.box[1]) +
                                  (tl.box[5] - tl.box[2]) * (tl.box[5] - tl.box[2])) : 0.f;
+    ctx->main_diag = nI ? sqrtf((tl.main_box[3] - tl.main_box[0]) * (tl.main_box[3] - tl.main_box[0]) + (tl.main_box[4] - tl.main_box[1]) * (tl.main_box[4] - tl.main_box[1]) +
+                                (tl.main_box[5] - tl.main_box[2]) * (tl.main_box[5] - tl.main_box[2])) : 0.f;
     ctx->stats.num_bvh_nodes = total_nodes;
     ctx->stats.num_bvh_triangles = tri_total;
     ctx->stats.num_tlas_instances = nI;
@@ -1134,10 +1147,13 @@ static int compute_ao_impl(AoBake* ctx, size_t begin, size_t end, int rays_per_s
     // or a previous attempt overflowed the deferred-ray list; fp32 under a TLAS (measured faster there)
     use_h2 = AOB_H2 != 0 && !force_fp32 && ctx->params.node_test != 1 && !ctx->two_level && ctx->unit_normals;
     // the far clamp of the fp32 node test is only needed when maxdist can actually cull inside the scene
-    const bool clamp = !(maxdist > 1.01f * ctx->scene_diag + fabsf(offset));
+    // (measured against the tree over the ORDINARY primitives: an oversized blocker on the extra root — the ground plane,
+    // 100 x the scene — must not switch the clamp on for the whole traversal; culling by tmax is an optimisation only)
+    const bool clamp = !(maxdist > 1.01f * ctx->main_diag + fabsf(offset));
     KernelT kern;
     if (use_h2)
-      kern = stats ? (KernelT)k_ao_persistent<true, false, false, true> : (KernelT)k_ao_persistent<false, false, false, true>;
+      kern = clamp ? (stats ? (KernelT)k_ao_persistent<true, false, true, true> : (KernelT)k_ao_persistent<false, false, true, true>)
+                   : (stats ? (KernelT)k_ao_persistent<true, false, false, true> : (KernelT)k_ao_persistent<false, false, false, true>);
     else if (clamp)
       kern = ctx->two_level ? (stats ? (KernelT)k_ao_persistent<true, true, true, false> : (KernelT)k_ao_persistent<false, true, true, false>)
                             : (stats ? (KernelT)k_ao_persistent<true, false, true, false> : (KernelT)k_ao_persistent<false, false, true, false>);
