@@ -132,6 +132,10 @@ typedef struct AoBakeParams {
                                      derivative)^2, the scale-free variant of round 1 (same null space, far better conditioned) */
   int32_t ls_matrix_free;         /* least-squares PCG product: 0 = A = M + wR assembled once (sliced ELL, no atomics per iteration;
                                      rows of vertices with too many neighbours stay matrix-free), 1 = matrix-free scatter */
+  int32_t ray_order;              /* fused kernel, the order in which a warp traces the rays of its 32-sample work item: 0 = default
+                                     (AOB_RAY_ORDER_DEFAULT of the build), 1 = sample-major (a lane owns a sample and walks its strata),
+                                     2 = stratum-major (the warp deals out the item's rays stratum by stratum: its 32 rays start on
+                                     neighbouring samples and point the same way).  Hit counts are identical either way. */
 } AoBakeParams;
 
 typedef struct AoTimings {        /* milliseconds, device-timed with CUDA events unless noted */

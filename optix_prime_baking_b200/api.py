@@ -39,7 +39,7 @@ EXPORTS = [
 class AoBakeParams(C.Structure):
     _fields_ = [("device", C.c_int32), ("instancing_mode", C.c_int32), ("cg_max_iterations", C.c_int32),
                 ("cg_tolerance", C.c_float), ("trace_kernel", C.c_int32), ("collect_stats", C.c_int32),
-                ("refill_below", C.c_int32), ("leaf_tris", C.c_int32), ("node_test", C.c_int32), ("deferred_capacity", C.c_int32), ("tri_batch", C.c_int32), ("no_oversized_split", C.c_int32), ("ls_energy", C.c_int32), ("ls_matrix_free", C.c_int32)]
+                ("refill_below", C.c_int32), ("leaf_tris", C.c_int32), ("node_test", C.c_int32), ("deferred_capacity", C.c_int32), ("tri_batch", C.c_int32), ("no_oversized_split", C.c_int32), ("ls_energy", C.c_int32), ("ls_matrix_free", C.c_int32), ("ray_order", C.c_int32)]
 
 
 class AoTimings(C.Structure):
@@ -126,7 +126,7 @@ class Baker:
     def __init__(self, device: int = 0, instancing_mode: int = INSTANCING_AUTO, collect_stats: bool = False,
                  cg_tolerance: float = 1e-6, cg_max_iterations: int = 20000, trace_kernel: int = 0,
                  refill_below: int = 0, leaf_tris: int = 0, node_test: int = 0, deferred_capacity: int = 0, tri_batch: int = 0,
-                 no_oversized_split: bool = False, ls_energy: int = 0, ls_matrix_free: bool = False):
+                 no_oversized_split: bool = False, ls_energy: int = 0, ls_matrix_free: bool = False, ray_order: int = 0):
         self.lib = load_library()
         p = default_params()
         p.device, p.instancing_mode, p.collect_stats = device, instancing_mode, int(collect_stats)
@@ -139,6 +139,7 @@ class Baker:
         p.no_oversized_split = int(no_oversized_split)
         p.ls_energy = ls_energy
         p.ls_matrix_free = int(ls_matrix_free)
+        p.ray_order = int(ray_order)
         self.device = device
         self._h = C.c_void_p()
         rc = self.lib.aobake_create(C.byref(p), C.byref(self._h))

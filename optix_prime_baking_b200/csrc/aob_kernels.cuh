@@ -541,7 +541,7 @@ AOB_D void defer_ray(const DeferredRays& D, uint32_t rel, uint32_t pass) {
   if (i < D.capacity) { U2 e; e.x = rel; e.y = pass; D.list[i] = e; }
 }
 
-template <bool STATS, bool TWO_LEVEL, bool CLAMP_TMAX, bool H2>
+template <bool STATS, bool TWO_LEVEL, bool CLAMP_TMAX, bool H2, bool PACKET>
 __global__ void __launch_bounds__(kAoBlock, 7) k_ao_persistent(BvhView bvh, SampleView S, uint64_t begin, uint32_t n, int q, float offset,
                                                              float maxdist, uint32_t n_chunks, uint32_t refill_below, uint32_t tri_batch,
                                                              uint32_t part, uint32_t num_parts, uint32_t sb_blocks, uint32_t n_local_blocks,
@@ -579,6 +579,40 @@ __global__ void __launch_bounds__(kAoBlock, 7) k_ao_persistent(BvhView bvh, Samp
   // per-lane item state
   __shared__ float s_la[kLookahead][6][kAoBlock];  // queued (lookahead) rays per thread: direction + slab reciprocals
   uint32_t la_count = 0, la_head = 0;              // rays queued; slot of the oldest
+  // PACKET (stratum-major ray order): the warp, not the lane, owns the work item (32 consecutive samples x a strata
+  // chunk) and deals its rays out in the order (stratum, sample): ray k of the item is stratum k / ns of sample k % ns.
+  // The 32 rays a warp traces at any time then start on neighbouring samples AND fall into the same one or two strata,
+  // i.e. point the same way to within a stratum cell and the samples' normals: they walk the same nodes, reach the
+  // same leaves in the same iteration (the triangle block runs for most of the warp) and end together.  Hits are
+  // counted per (item buffer, sample) in shared memory (16-bit halves: q^2 <= 65025) and written out when the buffer is
+  // retired; two items can be in flight (rays of the previous item still traversing while the next is dealt out).
+  static_assert(!PACKET || kLookahead == 1, "stratum-major order keeps one queued ray per lane");
+  __shared__ uint32_t s_pk_hits[PACKET ? kAoBlock / 32 : 1][2][16];
+  uint32_t pk_rel0_a = 0, pk_rel0_b = 0, pk_ns_a = 0, pk_ns_b = 0;   // warp-uniform: first sample / samples of the item in buffer 0 / 1 (ns == 0: free)
+  uint32_t pk_buf = 0, pk_next = 0, pk_end = 0, pk_pass0 = 0;   // warp-uniform: buffer being dealt out, next ray, rays, first stratum
+  uint32_t cur_tag = 0, la_tag = 0;   // (buffer << 5) | sample slot of the lane's active / queued ray
+  V3 la_org = v3(0, 0, 0);            // origin of the queued ray (the active one's is `org`)
+  if (PACKET) {
+    if (lane < 16u) { s_pk_hits[threadIdx.x >> 5][0][lane] = 0u; s_pk_hits[threadIdx.x >> 5][1][lane] = 0u; }
+    __syncwarp();
+  }
+  // retires item buffer b: its per-sample hit counts go to hits[] (every ray of the item has ended: the caller checked)
+  auto pk_flush = [&](uint32_t b) {
+    __syncwarp();
+    const uint32_t ns = b ? pk_ns_b : pk_ns_a, rel0 = b ? pk_rel0_b : pk_rel0_a;
+    if (ns != 0u) {
+      uint32_t* cnt = s_pk_hits[threadIdx.x >> 5][b];
+      if (lane < ns) {
+        const uint32_t v = (cnt[lane >> 1] >> (16u * (lane & 1u))) & 0xffffu;
+        if (n_chunks > 1) atomicAdd(&hits[rel0 + lane], v);
+        else hits[rel0 + lane] = v;
+      }
+      __syncwarp();
+      if (lane < 16u) cnt[lane] = 0u;
+      __syncwarp();
+      if (b) pk_ns_b = 0u; else pk_ns_a = 0u;
+    }
+  };
   bool have_item = false, ray_active = false, exhausted = false;
   uint32_t rel = 0, pass = 0, pass_end = 0, nh = 0;
   uint32_t supply_next = 0, supply_left = 0, supply_chunk = 0;  // warp-uniform
@@ -611,6 +645,7 @@ __global__ void __launch_bounds__(kAoBlock, 7) k_ao_persistent(BvhView bvh, Samp
     wdir = v3(la[0][threadIdx.x], la[1][threadIdx.x], la[2][threadIdx.x]);
     la_head = la_head + 1 == kLookahead ? 0u : la_head + 1;
     la_count--;
+    if (PACKET) { org = la_org; cur_tag = la_tag; }
     r.org = org; r.dir = wdir;
     r.idir = v3(la[3][threadIdx.x], la[4][threadIdx.x], la[5][threadIdx.x]);
     in_blas = !TWO_LEVEL;
@@ -622,6 +657,75 @@ __global__ void __launch_bounds__(kAoBlock, 7) k_ao_persistent(BvhView bvh, Samp
 
   while (true) {
     // ------------------------------ refill ------------------------------
+    if (PACKET) {
+      // every lane with an empty queue takes the next ray of the warp's item, in (stratum, sample) order
+      bool want = la_count == 0u;
+      while (true) {
+        const uint32_t want_mask = __ballot_sync(0xffffffffu, want);
+        if (want_mask == 0u) break;
+        if (pk_next == pk_end) {
+          if (exhausted) break;
+          // the next item goes into the other buffer; rays of the item before the current one may still be in flight
+          // there (only if one of them outlived a whole item: wait for it, correctness before the last percent)
+          const uint32_t nb = pk_buf ^ 1u;
+          const bool mine = (ray_active && (cur_tag >> 5) == nb) || (la_count != 0u && (la_tag >> 5) == nb);
+          if (__any_sync(0xffffffffu, mine)) break;
+          pk_flush(nb);
+          unsigned long long w = 0;
+          if (lane == 0) w = atomicAdd(counter, 1ull);
+          w = __shfl_sync(0xffffffffu, w, 0);
+          if (w >= total_items) { exhausted = true; break; }
+          const uint32_t chunk = (uint32_t)(w / n_blocks);  // chunk-major: concurrent warps work on neighbouring blocks
+          unsigned long long blk = w - (unsigned long long)chunk * n_blocks;
+          if (num_parts > 1) blk = ((blk / sb_blocks) * num_parts + part) * sb_blocks + blk % sb_blocks;
+          if (blk >= n_global_blocks) continue;  // padding block of a partial last super-block
+          const uint32_t ns = (uint32_t)min(32ull, (unsigned long long)n - blk * 32ull);
+          pk_pass0 = (uint32_t)(((uint64_t)chunk * q2) / n_chunks);
+          const uint32_t pe = (uint32_t)(((uint64_t)(chunk + 1) * q2) / n_chunks);
+          if (nb) { pk_rel0_b = (uint32_t)(blk * 32ull); pk_ns_b = ns; }
+          else { pk_rel0_a = (uint32_t)(blk * 32ull); pk_ns_a = ns; }
+          pk_buf = nb;
+          pk_next = 0u;
+          pk_end = ns * (pe - pk_pass0);
+          if (pk_end == 0u) continue;
+        }
+        const uint32_t my = (uint32_t)__popc(want_mask & lt_mask);
+        const uint32_t take = min((uint32_t)__popc(want_mask), pk_end - pk_next);
+        if (want && my < take) {
+          const uint32_t k = pk_next + my;
+          const uint32_t ns = pk_buf ? pk_ns_b : pk_ns_a;
+          const uint32_t st = ns == 32u ? k >> 5 : k / ns;
+          const uint32_t sl = k - st * ns;
+          const uint32_t rl = (pk_buf ? pk_rel0_b : pk_rel0_a) + sl, ps = pk_pass0 + st;
+          const uint64_t gf = 3ull * (begin + rl);
+          const V3 p = v3(__ldg(S.pos + gf), __ldg(S.pos + gf + 1), __ldg(S.pos + gf + 2));
+          const V3 nrm = v3(__ldg(S.nrm + gf), __ldg(S.nrm + gf + 1), __ldg(S.nrm + gf + 2));
+          const V3 fnrm = v3(__ldg(S.fnrm + gf), __ldg(S.fnrm + gf + 1), __ldg(S.fnrm + gf + 2));
+          const Onb ob = make_onb(nrm);
+          const V3 d = ao_ray_dir((uint32_t)(begin + rl), ps, q, nrm, fnrm, ob);
+          const V3 id = v3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
+          if (H2 && !(fmaxf(fmaxf(fabsf(id.x), fabsf(id.y)), fabsf(id.z)) <= kH2MaxIdir)) {
+            defer_ray(deferred, rl, ps);
+          } else {
+            float(*la)[kAoBlock] = s_la[0];
+            la[0][threadIdx.x] = d.x; la[1][threadIdx.x] = d.y; la[2][threadIdx.x] = d.z;
+            la[3][threadIdx.x] = id.x; la[4][threadIdx.x] = id.y; la[5][threadIdx.x] = id.z;
+            la_org = ao_ray_origin(p, nrm, offset);
+            la_tag = (pk_buf << 5) | sl;
+            la_head = 0u;
+            la_count = 1u;
+          }
+          want = false;   // (a lane whose ray was deferred takes its next one at the next refill)
+        }
+        pk_next += take;
+      }
+      if (!ray_active && la_count != 0u) start_queued();
+      if (!__any_sync(0xffffffffu, ray_active)) {
+        // nothing in flight: either rays are left to deal out (deferred ones used up this round's), or this is the end
+        if (exhausted && pk_next == pk_end) break;
+        continue;
+      }
+    } else {
     if (!ray_active && la_count == 0u && have_item && pass == pass_end) {
       if (n_chunks > 1) atomicAdd(&hits[rel], nh);
       else hits[rel] = nh;
@@ -698,6 +802,7 @@ __global__ void __launch_bounds__(kAoBlock, 7) k_ao_persistent(BvhView bvh, Samp
       if (exhausted && !__any_sync(0xffffffffu, have_item)) break;  // nothing in flight and nothing left
       continue;
     }
+    }   // (!PACKET)
 
     // ------------------------------ traverse ------------------------------
     // Triangle tests are batched across the warp.  A lane whose node test reports leaf hits does not
@@ -797,7 +902,11 @@ __global__ void __launch_bounds__(kAoBlock, 7) k_ao_persistent(BvhView bvh, Samp
             break;
           }
         }
-        nh += hit ? 1u : 0u;
+        if (PACKET) {
+          if (hit) atomicAdd(&s_pk_hits[threadIdx.x >> 5][cur_tag >> 5][(cur_tag & 31u) >> 1], 1u << (16u * (cur_tag & 1u)));
+        } else {
+          nh += hit ? 1u : 0u;
+        }
         if (done) {
           ray_active = false;
           if (la_count != 0u) start_queued();
@@ -807,11 +916,13 @@ __global__ void __launch_bounds__(kAoBlock, 7) k_ao_persistent(BvhView bvh, Samp
       if (act == 0u) break;
       if ((uint32_t)__popc(act) < refill_below) {
         // leave only if some idle lane can actually take a new ray
-        const bool can = !ray_active && ((have_item && pass < pass_end) || !exhausted);  // (a queued ray would already have started)
+        const bool can = !ray_active && (PACKET ? (pk_next < pk_end || !exhausted)
+                                                : ((have_item && pass < pass_end) || !exhausted));  // (a queued ray would already have started)
         if (__any_sync(0xffffffffu, can)) break;
       }
     }
   }
+  if (PACKET) { pk_flush(0u); pk_flush(1u); }
   if (STATS) {
     atomicAdd(&stats[0], (unsigned long long)c_nodes);
     atomicAdd(&stats[1], (unsigned long long)c_tris);

@@ -500,6 +500,26 @@ struct ScopedTimer {
   ~ScopedTimer() { c->timings.host_total_ms = (float)(now_ms() - t0); }
 };
 
+#ifndef AOB_RAY_ORDER_DEFAULT
+#define AOB_RAY_ORDER_DEFAULT 2
+#endif
+using AoKernelT = void (*)(BvhView, SampleView, uint64_t, uint32_t, int, float, float, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t,
+                           uint32_t, uint32_t*, unsigned long long*, unsigned long long*, DeferredRays);
+template <bool TWO_LEVEL, bool CLAMP, bool H2, bool PACKET>
+AoKernelT pick_ao_kernel_s(bool stats) {
+  return stats ? (AoKernelT)k_ao_persistent<true, TWO_LEVEL, CLAMP, H2, PACKET> : (AoKernelT)k_ao_persistent<false, TWO_LEVEL, CLAMP, H2, PACKET>;
+}
+template <bool PACKET>
+AoKernelT pick_ao_kernel_p(bool stats, bool two_level, bool clamp, bool h2) {
+  // the packed-fp16 node test exists for flattened scenes only
+  if (h2) return clamp ? pick_ao_kernel_s<false, true, true, PACKET>(stats) : pick_ao_kernel_s<false, false, true, PACKET>(stats);
+  if (two_level) return clamp ? pick_ao_kernel_s<true, true, false, PACKET>(stats) : pick_ao_kernel_s<true, false, false, PACKET>(stats);
+  return clamp ? pick_ao_kernel_s<false, true, false, PACKET>(stats) : pick_ao_kernel_s<false, false, false, PACKET>(stats);
+}
+AoKernelT pick_ao_kernel(bool stats, bool two_level, bool clamp, bool h2, bool packet) {
+  return packet ? pick_ao_kernel_p<true>(stats, two_level, clamp, h2) : pick_ao_kernel_p<false>(stats, two_level, clamp, h2);
+}
+
 }  // namespace
 
 // =========================================================================================
@@ -524,6 +544,7 @@ int aobake_default_params(AoBakeParams* p) {
   p->no_oversized_split = 0;
   p->ls_energy = 0;
   p->ls_matrix_free = 0;
+  p->ray_order = 0;
   return AOBAKE_OK;
 }
 
@@ -1141,8 +1162,7 @@ static int compute_ao_impl(AoBake* ctx, size_t begin, size_t end, int rays_per_s
   } else {
     // persistent variant: one resident wave of CTAs (a multiple of the SM count), dynamic work fetch
     if (n > 0xfffffff0ull) return ctx->fail(AOBAKE_ERR_INVALID_ARGUMENT, "more than 2^32 samples in one range");
-    using KernelT = void (*)(BvhView, SampleView, uint64_t, uint32_t, int, float, float, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t,
-                             uint32_t, uint32_t*, unsigned long long*, unsigned long long*, DeferredRays);
+    using KernelT = AoKernelT;
     // node test: packed fp16 (two planes per instruction) for flattened scenes, unless asked otherwise
     // or a previous attempt overflowed the deferred-ray list; fp32 under a TLAS (measured faster there)
     use_h2 = AOB_H2 != 0 && !force_fp32 && ctx->params.node_test != 1 && !ctx->two_level && ctx->unit_normals;
@@ -1150,16 +1170,9 @@ static int compute_ao_impl(AoBake* ctx, size_t begin, size_t end, int rays_per_s
     // (measured against the tree over the ORDINARY primitives: an oversized blocker on the extra root — the ground plane,
     // 100 x the scene — must not switch the clamp on for the whole traversal; culling by tmax is an optimisation only)
     const bool clamp = !(maxdist > 1.01f * ctx->main_diag + fabsf(offset));
-    KernelT kern;
-    if (use_h2)
-      kern = clamp ? (stats ? (KernelT)k_ao_persistent<true, false, true, true> : (KernelT)k_ao_persistent<false, false, true, true>)
-                   : (stats ? (KernelT)k_ao_persistent<true, false, false, true> : (KernelT)k_ao_persistent<false, false, false, true>);
-    else if (clamp)
-      kern = ctx->two_level ? (stats ? (KernelT)k_ao_persistent<true, true, true, false> : (KernelT)k_ao_persistent<false, true, true, false>)
-                            : (stats ? (KernelT)k_ao_persistent<true, false, true, false> : (KernelT)k_ao_persistent<false, false, true, false>);
-    else
-      kern = ctx->two_level ? (stats ? (KernelT)k_ao_persistent<true, true, false, false> : (KernelT)k_ao_persistent<false, true, false, false>)
-                            : (stats ? (KernelT)k_ao_persistent<true, false, false, false> : (KernelT)k_ao_persistent<false, false, false, false>);
+    // ray order within a work item: stratum-major (the warp's rays share origin neighbourhood AND direction) or sample-major
+    const bool packet = (ctx->params.ray_order == 0 ? AOB_RAY_ORDER_DEFAULT : ctx->params.ray_order) == 2;
+    KernelT kern = pick_ao_kernel(stats, ctx->two_level, clamp, use_h2, packet);
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kAoBlock, 0));
     if (per_sm < 1) per_sm = 1;

@@ -459,6 +459,36 @@ def test_interleaved_parts_sum_to_full_bake(api, name, parts, block):
         assert np.array_equal(acc.view(np.uint32), want.view(np.uint32))
 
 
+@pytest.mark.parametrize("name", ["sphere_ground", "heightfield", "instanced"])
+@pytest.mark.parametrize("rays", [1, 9, 64, 100, 1024])
+def test_ray_orders_give_identical_hit_counts(api, name, rays):
+    """The fused kernel traces the rays of a work item sample-major (a lane owns a sample) or stratum-major (the warp
+    deals the item's rays out stratum by stratum; hits counted per sample in shared memory).  The order changes which
+    rays share a warp, never a ray: per-sample hit counts must be identical, and equal to the one-ray-per-thread kernel's
+    — for a sample count that is not a multiple of 32, single-ray items (rays = 1: every refill crosses an item
+    boundary), non-power-of-two strata, and as interleaved parts."""
+    scene, blockers = SCENES[name]
+    off, maxd = scenes.default_distances(scene)
+    res = {}
+    for key, kw in (("simple", dict(trace_kernel=1)), ("sample_major", dict(trace_kernel=2, ray_order=1)),
+                    ("stratum_major", dict(trace_kernel=2, ray_order=2))):
+        with api.Baker(**kw) as bk:
+            bk.set_scene(scene, blockers)
+            total, per = bk.distribute_samples(1, 10007)
+            bk.sample_instances(per, 1, download=False)
+            bk.compute_ao(rays, off, maxd, download=False)
+            res[key] = bk.hit_counts()
+            if key != "simple":
+                acc = np.zeros(total, dtype=np.int64)
+                for p in range(3):
+                    bk.compute_ao_interleaved(p, 3, rays, off, maxd, block_samples=96)
+                    acc += bk.hit_counts()
+                assert np.array_equal(acc, res[key].astype(np.int64))
+    assert res["simple"].sum() > 0
+    assert np.array_equal(res["sample_major"], res["simple"])
+    assert np.array_equal(res["stratum_major"], res["simple"])
+
+
 @pytest.mark.parametrize("scale,offset,seed", [(1.0, 0.0, 1), (1e-3, 0.0, 2), (1e3, 0.0, 3), (1.0, 5e3, 4), (0.05, -2e4, 5)])
 def test_fuzz_triangle_soups_match_brute_force(api, scale, offset, seed):
     """Random triangle soups (slivers, tiny and huge triangles, scenes far from the origin) and random
