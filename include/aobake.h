@@ -123,7 +123,8 @@ typedef struct AoBakeParams {
                                      aobake_compute_ao repeat the launch with the fp32 kernels — settable so that tests can force it */
   int32_t tri_batch;              /* fused kernel: low byte = lanes of a warp that must hold leaf hits before the warp runs its
                                      triangle block (paused lanes take no node steps meanwhile; 1 = test at once); next byte =
-                                     the most iterations a paused lane waits (0 = no limit); 0 = default (8 lanes flattened, 12 under a TLAS; 6 iterations) */
+                                     the most iterations a paused lane waits (0 = no limit); 0 = default (16 lanes flattened — 8 with
+                                     ray_order 1 — 12 under a TLAS; 6 iterations) */
   int32_t no_oversized_split;     /* BVH build: 0 = primitives (or TLAS instances) spanning more than a quarter of the scene (a ground
                                      plane under a fine mesh) are kept out of the tree and hang off one extra root node; 1 = build
                                      one tree over everything (A/B switch; both give the same hits) */
@@ -135,7 +136,8 @@ typedef struct AoBakeParams {
   int32_t ray_order;              /* fused kernel, the order in which a warp traces the rays of its 32-sample work item: 0 = default
                                      (AOB_RAY_ORDER_DEFAULT of the build), 1 = sample-major (a lane owns a sample and walks its strata),
                                      2 = stratum-major (the warp deals out the item's rays stratum by stratum: its 32 rays start on
-                                     neighbouring samples and point the same way).  Hit counts are identical either way. */
+                                     neighbouring samples and come from one or two strata; whichever lane is free takes the next ray).
+                                     Hit counts are identical either way. */
 } AoBakeParams;
 
 typedef struct AoTimings {        /* milliseconds, device-timed with CUDA events unless noted */

@@ -580,10 +580,13 @@ __global__ void __launch_bounds__(kAoBlock, 7) k_ao_persistent(BvhView bvh, Samp
   __shared__ float s_la[kLookahead][6][kAoBlock];  // queued (lookahead) rays per thread: direction + slab reciprocals
   uint32_t la_count = 0, la_head = 0;              // rays queued; slot of the oldest
   // PACKET (stratum-major ray order): the warp, not the lane, owns the work item (32 consecutive samples x a strata
-  // chunk) and deals its rays out in the order (stratum, sample): ray k of the item is stratum k / ns of sample k % ns.
-  // The 32 rays a warp traces at any time then start on neighbouring samples AND fall into the same one or two strata,
-  // i.e. point the same way to within a stratum cell and the samples' normals: they walk the same nodes, reach the
-  // same leaves in the same iteration (the triangle block runs for most of the warp) and end together.  Hits are
+  // chunk) and deals its rays out in the order (stratum, sample): ray k of the item is stratum k / ns of sample k % ns,
+  // and whichever lane has room takes the next one.  No lane is tied to a sample any more, so there is no per-lane
+  // item state to set up, no sample whose expensive rays hold one lane back while the others run ahead, and ray
+  // generation runs with nearly the whole warp (27.8 lanes against 19.5); the 32 rays in flight start on neighbouring
+  // samples and come from one or two strata.  Measured +7 % / +13 % / +9 % on configs 2 / 3 / 1 (profiles/r2/
+  // sweep_ray_order.log); it is the DEALING that pays — turning the strata so that one stratum is one world direction for
+  // the whole warp, or making the whole GPU shoot into one sector at a time, added nothing.  Hits are
   // counted per (item buffer, sample) in shared memory (16-bit halves: q^2 <= 65025) and written out when the buffer is
   // retired; two items can be in flight (rays of the previous item still traversing while the next is dealt out).
   static_assert(!PACKET || kLookahead == 1, "stratum-major order keeps one queued ray per lane");

@@ -228,7 +228,7 @@ constexpr uint32_t kDefaultBlockSamples = 16384;   // super-block of the interle
 #define AOB_ITEMS_PER_WARP 32
 #endif
 constexpr uint32_t kItemsPerWarp = AOB_ITEMS_PER_WARP;
-constexpr uint32_t kTriBatchFlat = 8 | (6 << 8), kTriBatchTwoLevel = 12 | (6 << 8);   // default AoBakeParams::tri_batch (sweep: profiles/r2/sweep_tri_batch.log)
+constexpr uint32_t kTriBatchFlat = 8 | (6 << 8), kTriBatchFlatPacket = 16 | (6 << 8), kTriBatchTwoLevel = 12 | (6 << 8);   // default AoBakeParams::tri_batch (sweep: profiles/r2/sweep_tri_batch.log)
 
 // Makes a local status collective: every rank of the communicator calls this once at the same point
 // with its own status; all of them return non-zero if any rank failed, so that no rank enters the
@@ -1199,7 +1199,8 @@ static int compute_ao_impl(AoBake* ctx, size_t begin, size_t end, int rays_per_s
     const uint32_t refill = ctx->params.refill_below > 0 ? (uint32_t)ctx->params.refill_below : 28u;
     // lanes that must hold leaf hits before the warp runs its triangle block (1 = test at once)
     // tri_batch = lanes | iterations << 8 (the longest a paused lane waits); iterations 0 => no limit
-    uint32_t tri_batch = ctx->params.tri_batch > 0 ? (uint32_t)ctx->params.tri_batch : (ctx->two_level ? kTriBatchTwoLevel : kTriBatchFlat);
+    uint32_t tri_batch = ctx->params.tri_batch > 0 ? (uint32_t)ctx->params.tri_batch
+                                                   : (ctx->two_level ? kTriBatchTwoLevel : (packet ? kTriBatchFlatPacket : kTriBatchFlat));
     {
       const uint32_t lanes = std::min(std::max(tri_batch & 0xffu, 1u), 32u), wait = (tri_batch >> 8) & 0xffu;
       tri_batch = lanes | ((wait ? wait : 255u) << 8);

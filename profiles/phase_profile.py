@@ -55,7 +55,8 @@ def kline(pat):
 
 
 K = {"kernel_begin": kline("k_ao_persistent(BvhView bvh"), "start_queued": kline("auto start_queued = [&]()"), "refill": kline("// ------------------------------ refill"),
-     "lookahead": kline("if (have_item && !la_valid && pass < pass_end)"), "after_lookahead": kline("if (!ray_active && la_valid) start_queued();"),
+     "lookahead": kline("const uint32_t my = (uint32_t)__popc(want_mask & lt_mask);") or kline("if (have_item && !la_valid && pass < pass_end)"),   # (stratum-major kernel: the deal-out block generates the rays)
+     "after_lookahead": kline("if (!ray_active && la_count != 0u) start_queued();") or kline("if (!ray_active && la_valid) start_queued();"),
      "traverse": kline("// ------------------------------ traverse"), "tri_block": kline("const uint32_t pm = __ballot_sync(0xffffffffu, paused);") or kline("bool hit = false;"),   # (round-1 kernel: tests in place)
      "pop": kline("// Ray end and restart are written once"), "loop_end": kline("act = __ballot_sync(0xffffffffu, ray_active);   // (unchanged") or kline("const uint32_t act = __ballot_sync(0xffffffffu, ray_active);"), "kernel_end": kline("// The rays k_ao_persistent<.., H2 = true> set aside")}
 
