@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """One compute_ao over a bounded sample range of a workload — the short command wrapped by ncu.
-usage: run_range.py <c1|c2|c3|c4> <num_samples or 0 = all> [trace_kernel] [repeats] [start_fraction]"""
+usage: run_range.py <c1|c2|c3|c4> <num_samples or 0 = all> [trace_kernel] [repeats] [start_fraction]
+(environment: RAY_ORDER = AoBakeParams::ray_order, TRI_BATCH = AoBakeParams::tri_batch)"""
+import os
 import sys
 
 sys.path.insert(0, ".")
@@ -15,7 +17,7 @@ frac = float(sys.argv[5]) if len(sys.argv) > 5 else 0.37
 scene, blockers, min_per, requested, desc = bench.make_workload(w)
 rays = bench.RAYS[w]
 off, maxd = scenes.default_distances(scene)
-with api.Baker(trace_kernel=tk) as bk:
+with api.Baker(trace_kernel=tk, ray_order=int(os.environ.get("RAY_ORDER", "0")), tri_batch=int(os.environ.get("TRI_BATCH", "0"))) as bk:
     bk.set_scene(scene, blockers)
     total, per = bk.distribute_samples(min_per, requested)
     bk.sample_instances(per, min_per, download=False)
