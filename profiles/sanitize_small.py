@@ -29,7 +29,7 @@ for name, (scene, blockers) in {"sphere": scenes.config1_sphere(20, 20),
             bk.compute_ao_distributed(16, off, maxd)
             v3 = bk.map_ao_to_vertices(api.FILTER_LEAST_SQUARES, 0.1, distributed=True)
             bk.comm_destroy()
-        with api.Baker(trace_kernel=tk, ls_matrix_free=True, ls_energy=1, tri_batch=1, no_oversized_split=True) as bk:
+        with api.Baker(trace_kernel=tk, ray_order=1, ls_matrix_free=True, ls_energy=1, tri_batch=1, no_oversized_split=True) as bk:
             bk.set_scene(scene, blockers)
             bk.set_samples(sb, per)
             bk.compute_ao(16, off, maxd, download=False)
