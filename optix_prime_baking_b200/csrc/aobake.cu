@@ -566,6 +566,10 @@ int aobake_create(const AoBakeParams* params, AoBake** out) {
     g_create_error = "device ordinal out of range";
     return AOBAKE_ERR_INVALID_ARGUMENT;
   }
+  if (p.ray_order < 0 || p.ray_order > 2 || p.trace_kernel < 0 || p.trace_kernel > 2) {
+    g_create_error = "ray_order and trace_kernel must be 0, 1 or 2";
+    return AOBAKE_ERR_INVALID_ARGUMENT;
+  }
   if ((e = cudaSetDevice(p.device)) != cudaSuccess) {
     g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
     return AOBAKE_ERR_CUDA;

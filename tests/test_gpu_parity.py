@@ -294,6 +294,9 @@ def test_closed_box_is_fully_occluded_and_lone_triangle_is_open(api):
 
 def test_edge_cases(api):
     scene, blockers = SCENES["sphere_ground"]
+    for bad in (dict(ray_order=3), dict(ray_order=-1), dict(trace_kernel=5)):
+        with pytest.raises(api.AoBakeError):       # kernel selectors outside their range are rejected at create
+            api.Baker(**bad)
     with api.Baker() as bk:
         with pytest.raises(api.AoBakeError):
             bk.compute_ao(64, 0.1, 1.0)           # no scene yet
