@@ -43,6 +43,7 @@ from optix_prime_baking_b200 import scenes  # noqa: E402
 
 RAYS = {"c1": 64, "c2": 256, "c3": 1024, "c4": 256, "c5": 1024}
 BLOCK_SAMPLES = 16384
+TRAVERSAL_NAMES = {1: "binary SAH BVH, scalar slab test", 2: "SAH BVH collapsed 8-wide, AVX2 slab test, nearest child first"}
 PROFILE_ROUND = "r2"
 
 
@@ -181,9 +182,10 @@ def cpu_baseline(scene, blockers, samples, rays, off, maxd, pilot_rays=12_000_00
     """The oracle (kind 'port': the reference cannot be compiled) on all host cores, on a
     bounded, evenly strided subset of the workload's samples: a short pilot sizes the timed sample
     for about `target_seconds` of CPU work (the whole workload if that is less)."""
-    from tests.oracle_binding import Oracle, lib
+    from tests.oracle_binding import Oracle, lib, set_traversal
     use_all_host_cores()
     q = sqrt_rays(rays)
+    walk = TRAVERSAL_NAMES[set_traversal(0)]   # 8-wide AVX2 where the host CPU has it (what a production CPU tracer does), else binary scalar
     orc = Oracle(scene, blockers)
     t0 = time.perf_counter()
     _ = orc.tracer
@@ -202,7 +204,7 @@ def cpu_baseline(scene, blockers, samples, rays, off, maxd, pilot_rays=12_000_00
     dt = time.perf_counter() - t0
     cores = lib().ao_oracle_num_threads()
     orc.close()
-    return {"value": n_sub * q * q / dt / 1e6, "unit": "Mrays/s", "cores": int(cores), "kind": "port",
+    return {"value": n_sub * q * q / dt / 1e6, "unit": "Mrays/s", "cores": int(cores), "kind": "port", "traversal": walk,
             "sample": f"{n_sub} evenly strided samples x {q * q} rays = {n_sub * q * q} rays of the same workload, {dt:.1f} s "
                       f"(oracle BVH build {t_build:.1f} s excluded; sized by a {n_pilot * q * q}-ray pilot)", "seconds": dt}
 
@@ -215,8 +217,9 @@ def run_reference(args, rank, world):
     scene, blockers, min_per, requested, desc = make_workload(args.workload)
     rays = RAYS[args.workload]
     off, maxd = scenes.default_distances(scene)
-    from tests.oracle_binding import Oracle, lib
+    from tests.oracle_binding import Oracle, lib, set_traversal
     use_all_host_cores()
+    walk = TRAVERSAL_NAMES[set_traversal(0)]
     orc = Oracle(scene, blockers)
     total, per = orc.distribute_samples(min_per, requested)
     samples = orc.sample_instances(per, min_per)
@@ -248,7 +251,7 @@ def run_reference(args, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc, "note": "reference sources absent (SURVEY.md §0): CPU oracle port on host cores"},
-        "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": cores, "kind": "port", "traversal": walk, "sample": sample},
         "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 

@@ -16,6 +16,10 @@
 // could not settle a detail the choice made here is normative (DESIGN.md "Oracle
 // decisions").
 //
+// Two walks of the same SAH tree answer the any-hit query — binary with a scalar slab test, and (where the CPU has AVX2,
+// chosen at run time) the tree collapsed 8-wide with an 8-lane slab test of the same arithmetic — and return the same
+// answer for every ray; the wide one exists so that bench.py's CPU arm is a fair yardstick, not a naive one.
+//
 // Build: g++ -O2 -fopenmp -ffp-contract=off -shared -fPIC  (see oracle/Makefile).
 // -ffp-contract=off matters: every fp32/fp64 expression below is evaluated exactly as
 // written (one IEEE rounding per operation, left to right), which is what the CUDA path
@@ -32,6 +36,12 @@
 #include <vector>
 #ifdef _OPENMP
 #include <omp.h>
+#endif
+#if defined(__x86_64__) && (defined(__GNUC__) || defined(__clang__))
+#include <immintrin.h>
+#define AO_ORACLE_HAVE_AVX2_PATH 1
+#else
+#define AO_ORACLE_HAVE_AVX2_PATH 0
 #endif
 
 // ----------------------------------------------------------------------------------
@@ -354,10 +364,34 @@ struct BNode {
   uint32_t left;   // internal: index of left child (right = left+1); leaf: first prim
   uint32_t count;  // 0 => internal
 };
+// 8-wide collapse of the binary tree for the AVX2 traversal (below): child boxes in SoA form, one 8-lane slab test per
+// node.  A slot is empty (cnt == 0), a leaf (cnt = 1..4 primitives from prim[ref]) or an internal child (cnt == kWideInternal,
+// ref = index of the wide node).  Every box is the box of a node of the binary tree, unchanged.
+constexpr uint32_t kWideInternal = 0xffffffffu;
+struct alignas(32) WNode {
+  float lo[3][8], hi[3][8];
+  uint32_t ref[8], cnt[8];
+};
 struct Bvh {
   std::vector<BNode> nodes;
   std::vector<uint32_t> prim;  // permutation
+  std::vector<WNode> wide;     // empty: binary traversal only
 };
+// Traversal used by TriSoup::any_hit: 0 = auto (8-wide AVX2 where the CPU has it, else binary scalar), 1 = binary scalar,
+// 2 = 8-wide AVX2 (binary if the CPU lacks AVX2).  Both walk boxes of the same SAH tree with the same slab arithmetic and
+// test triangles with the same scalar watertight test, so they return the same answer for every ray (any-hit does not
+// depend on the order of the walk); the wide one is what a production CPU tracer does and is the fairer yardstick for
+// bench.py's CPU arm.
+int g_traversal_mode = 0;
+bool cpu_has_avx2() {
+#if AO_ORACLE_HAVE_AVX2_PATH
+  static const bool ok = __builtin_cpu_supports("avx2");
+  return ok;
+#else
+  return false;
+#endif
+}
+bool use_wide_traversal() { return g_traversal_mode != 1 && cpu_has_avx2(); }
 void bvh_build(const std::vector<Box>& pb, Bvh& out) {
   const uint32_t n = (uint32_t)pb.size();
   out.prim.resize(n);
@@ -437,6 +471,55 @@ void bvh_build(const std::vector<Box>& pb, Bvh& out) {
   }
 }
 
+// Collapses the binary tree into 8-wide nodes: starting from a node's two children, the internal slot with the largest
+// surface area is opened (replaced by its two children) until eight slots are filled or only leaves remain.
+void bvh_build_wide(Bvh& bvh) {
+  bvh.wide.clear();
+  if (bvh.nodes.empty()) return;
+  struct Item { uint32_t bnode, wnode; };
+  std::vector<Item> todo;
+  bvh.wide.push_back(WNode());
+  todo.push_back({0u, 0u});
+  while (!todo.empty()) {
+    const Item it = todo.back();
+    todo.pop_back();
+    uint32_t slots[8];
+    int ns = 0;
+    const BNode& root = bvh.nodes[it.bnode];
+    if (root.count) slots[ns++] = it.bnode;   // a tree that is a single leaf
+    else { slots[ns++] = root.left; slots[ns++] = root.left + 1; }
+    while (ns < 8) {
+      int best = -1;
+      float best_area = -1.0f;
+      for (int k = 0; k < ns; k++) {
+        const BNode& c = bvh.nodes[slots[k]];
+        if (c.count == 0 && c.box.half_area() > best_area) { best_area = c.box.half_area(); best = k; }
+      }
+      if (best < 0) break;
+      const uint32_t l = bvh.nodes[slots[best]].left;
+      slots[best] = l;
+      slots[ns++] = l + 1;
+    }
+    WNode w;
+    for (int k = 0; k < 8; k++) {
+      for (int a = 0; a < 3; a++) { w.lo[a][k] = std::numeric_limits<float>::max(); w.hi[a][k] = -std::numeric_limits<float>::max(); }
+      w.ref[k] = 0; w.cnt[k] = 0;
+    }
+    for (int k = 0; k < ns; k++) {
+      const BNode& c = bvh.nodes[slots[k]];
+      for (int a = 0; a < 3; a++) { w.lo[a][k] = c.box.lo[a]; w.hi[a][k] = c.box.hi[a]; }
+      if (c.count) { w.ref[k] = c.left; w.cnt[k] = c.count; }
+      else {
+        w.cnt[k] = kWideInternal;
+        w.ref[k] = (uint32_t)bvh.wide.size();
+        bvh.wide.push_back(WNode());
+        todo.push_back({slots[k], w.ref[k]});
+      }
+    }
+    bvh.wide[it.wnode] = w;
+  }
+}
+
 struct TriSoup {
   std::vector<V3> v;  // 3 per triangle
   Bvh bvh;
@@ -448,8 +531,86 @@ struct TriSoup {
       pb[t].grow(v[3 * t]); pb[t].grow(v[3 * t + 1]); pb[t].grow(v[3 * t + 2]);
     }
     bvh_build(pb, bvh);
+    if (cpu_has_avx2()) {
+      bvh_build_wide(bvh);
+      // the wide walk reads a leaf's triangles from one contiguous run (leaf order) instead of through prim[]
+      vleaf.resize(v.size());
+#pragma omp parallel for schedule(static)
+      for (int64_t i = 0; i < (int64_t)bvh.prim.size(); i++) {
+        const uint32_t t = bvh.prim[i];
+        vleaf[3 * i] = v[3 * t]; vleaf[3 * i + 1] = v[3 * t + 1]; vleaf[3 * i + 2] = v[3 * t + 2];
+      }
+    }
   }
+  std::vector<V3> vleaf;   // the triangles in leaf order (8-wide walk only)
+#if AO_ORACLE_HAVE_AVX2_PATH
+  // The 8-lane form of box_hit: the same operations in the same order per lane ((plane - origin) * reciprocal, NaN planes
+  // skipped, far distance padded by the same factor), so a lane decides exactly as box_hit does for that box.
+  __attribute__((target("avx2"))) bool any_hit_wide(const Ray& r) const {
+    const RayShear sh = make_shear(r.d);
+    const __m256 o[3] = {_mm256_set1_ps(r.o.x), _mm256_set1_ps(r.o.y), _mm256_set1_ps(r.o.z)};
+    const __m256 iv[3] = {_mm256_set1_ps(1.0f / r.d.x), _mm256_set1_ps(1.0f / r.d.y), _mm256_set1_ps(1.0f / r.d.z)};
+    const __m256 tmin = _mm256_set1_ps(r.tmin), tmax = _mm256_set1_ps(r.tmax), pad = _mm256_set1_ps(1.0000005f);
+    uint32_t stack[256];
+    int sp = 0;
+    stack[sp++] = 0;
+    while (sp) {
+      const WNode& n = bvh.wide[stack[--sp]];
+      __m256 tn = tmin, tf = tmax;
+      for (int k = 0; k < 3; k++) {
+        const __m256 t0 = _mm256_mul_ps(_mm256_sub_ps(_mm256_load_ps(n.lo[k]), o[k]), iv[k]);
+        const __m256 t1 = _mm256_mul_ps(_mm256_sub_ps(_mm256_load_ps(n.hi[k]), o[k]), iv[k]);
+        const __m256 nan = _mm256_or_ps(_mm256_cmp_ps(t0, t0, _CMP_UNORD_Q), _mm256_cmp_ps(t1, t1, _CMP_UNORD_Q));
+        const __m256 lt = _mm256_cmp_ps(t0, t1, _CMP_LT_OQ);
+        const __m256 a = _mm256_blendv_ps(t1, t0, lt), c = _mm256_blendv_ps(t0, t1, lt);
+        const __m256 tn2 = _mm256_blendv_ps(tn, a, _mm256_cmp_ps(a, tn, _CMP_GT_OQ));
+        const __m256 tf2 = _mm256_blendv_ps(tf, c, _mm256_cmp_ps(c, tf, _CMP_LT_OQ));
+        tn = _mm256_blendv_ps(tn2, tn, nan);
+        tf = _mm256_blendv_ps(tf2, tf, nan);
+      }
+      unsigned mask = (unsigned)_mm256_movemask_ps(_mm256_cmp_ps(tn, _mm256_mul_ps(tf, pad), _CMP_LE_OQ));
+      if (!mask) continue;
+      alignas(32) float tnear[8];
+      _mm256_store_ps(tnear, tn);
+      // leaves are tested at once (a hit ends the ray); internal children go on the stack with the nearest one on top —
+      // an occluded ray usually finds its blocker in the first subtree it enters (the order never changes the answer)
+      uint32_t nearest = 0xffffffffu;
+      float nearest_t = std::numeric_limits<float>::infinity();
+      while (mask) {
+        const int k = __builtin_ctz(mask);
+        mask &= mask - 1u;
+        const uint32_t cnt = n.cnt[k];
+        if (cnt == 0u) continue;
+        if (cnt == kWideInternal) {
+          if (sp >= 255) return any_hit_binary(r);   // unreachable for SAH trees; the binary walk has its own guard
+          const char* nx = reinterpret_cast<const char*>(&bvh.wide[n.ref[k]]);   // 4 cache lines; the walk is latency bound on big scenes
+          _mm_prefetch(nx, _MM_HINT_T0); _mm_prefetch(nx + 64, _MM_HINT_T0); _mm_prefetch(nx + 128, _MM_HINT_T0); _mm_prefetch(nx + 192, _MM_HINT_T0);
+          if (tnear[k] < nearest_t) {
+            if (nearest != 0xffffffffu) stack[sp++] = nearest;
+            nearest = n.ref[k];
+            nearest_t = tnear[k];
+          } else {
+            stack[sp++] = n.ref[k];
+          }
+        } else {
+          const V3* tv = &vleaf[3ull * n.ref[k]];
+          for (uint32_t i = 0; i < cnt; i++)
+            if (woop_hit(r, sh, tv[3 * i], tv[3 * i + 1], tv[3 * i + 2], nullptr, nullptr)) return true;
+        }
+      }
+      if (nearest != 0xffffffffu) stack[sp++] = nearest;
+    }
+    return false;
+  }
+#endif
   bool any_hit(const Ray& r) const {
+    if (bvh.nodes.empty() || v.empty()) return false;
+#if AO_ORACLE_HAVE_AVX2_PATH
+    if (!bvh.wide.empty() && use_wide_traversal()) return any_hit_wide(r);
+#endif
+    return any_hit_binary(r);
+  }
+  bool any_hit_binary(const Ray& r) const {
     if (bvh.nodes.empty() || v.empty()) return false;
     RayShear sh = make_shear(r.d);
     V3 id = v3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
@@ -846,6 +1007,12 @@ void* ao_oracle_tracer_create(const OrScene* scene, const OrScene* blockers, int
   return T;
 }
 void ao_oracle_tracer_destroy(void* h) { delete static_cast<Tracer*>(h); }
+// Traversal of the triangle BVHs: 0 = auto, 1 = binary scalar, 2 = 8-wide AVX2 (see g_traversal_mode).  Returns the kind in
+// effect for tracers built on this CPU: 1 = binary scalar, 2 = 8-wide AVX2.
+int ao_oracle_set_traversal(int mode) {
+  g_traversal_mode = (mode == 1 || mode == 2) ? mode : 0;
+  return use_wide_traversal() ? 2 : 1;
+}
 int ao_oracle_tracer_is_two_level(void* h) { return static_cast<Tracer*>(h)->two_level ? 1 : 0; }
 
 // rays: n x 8 floats (o.xyz, tmin, d.xyz, tmax).  hit: n bytes (1 = occluded).

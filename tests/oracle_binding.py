@@ -56,8 +56,19 @@ def lib():
         L.ao_oracle_make_ground_plane.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float,
                                                   C.c_void_p, C.c_void_p]
         L.ao_oracle_affine_inverse.argtypes = [C.c_void_p, C.c_void_p]
+        L.ao_oracle_set_traversal.argtypes = [C.c_int]
+        L.ao_oracle_set_traversal.restype = C.c_int
         _LIB = L
     return _LIB
+
+
+TRAVERSAL_AUTO, TRAVERSAL_BINARY, TRAVERSAL_WIDE = 0, 1, 2
+
+
+def set_traversal(mode: int = TRAVERSAL_AUTO) -> int:
+    """Traversal of the oracle's triangle BVHs (process-wide): 0 = auto, 1 = binary scalar, 2 = 8-wide AVX2.  Returns the
+    kind in effect on this CPU (1 or 2); both give the same answer for every ray."""
+    return int(lib().ao_oracle_set_traversal(int(mode)))
 
 
 def tea(rounds, v0, v1):

@@ -154,8 +154,16 @@ def test_oracle_bvh_vs_brute_force(mode):
     scene, blk = scenes.config4_instanced(grid=2, stacks=10, slices=10, with_ground=True)
     orc = Oracle(scene, blk, mode)
     rays = _random_rays(scene, 20000, 3)
-    a, b = orc.trace_rays(rays), orc.trace_rays(rays, brute=True)
-    assert np.array_equal(a, b) and 0.02 < a.mean() < 0.98
+    b = orc.trace_rays(rays, brute=True)
+    kinds = set()
+    try:   # both walks of the oracle (binary scalar, 8-wide AVX2 where the CPU has it) against brute force
+        for trav in (ob.TRAVERSAL_BINARY, ob.TRAVERSAL_WIDE):
+            kinds.add(ob.set_traversal(trav))
+            a = orc.trace_rays(rays)
+            assert np.array_equal(a, b) and 0.02 < a.mean() < 0.98
+    finally:
+        ob.set_traversal(ob.TRAVERSAL_AUTO)
+    assert 1 in kinds
 
 
 def _world_tris(scene_list):
@@ -336,7 +344,12 @@ def test_fuzz_quantised_traversal_is_conservative(emu, scale, offset, seed):
     mesh = Mesh(tri.reshape(-1, 3), np.arange(3 * n, dtype=np.uint32).reshape(n, 3))
     orc = Oracle(Scene([mesh], [Instance(0)]))
     want = orc.trace_rays(rays, brute=True)
-    assert np.array_equal(orc.trace_rays(rays), want)                                      # the oracle's own BVH
+    try:                                                                                   # the oracle's own BVH, both walks
+        for trav in (ob.TRAVERSAL_BINARY, ob.TRAVERSAL_WIDE):
+            ob.set_traversal(trav)
+            assert np.array_equal(orc.trace_rays(rays), want), trav
+    finally:
+        ob.set_traversal(ob.TRAVERSAL_AUTO)
     B = emu.emu_bvh_create_flat(tri.ctypes.data, n)
     emu.emu_trace.restype = C.c_uint64
     visits = []
